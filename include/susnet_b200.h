@@ -1,0 +1,233 @@
+/*
+ * susnet_b200.h -- C ABI of the B200-native batched Sus-Net simulator + observation encoder.
+ *
+ * The reference (jhrudden/Sus-Net) is pure Python and has no FFI of its own; the drop-in boundary is the
+ * duck-typed surface its callers use.  Each entry point below names the reference
+ * interface it replaces (file:line under the reference's src/).  The Python host side
+ * (sus_net_b200/env.py, featurizers.py) binds these with ctypes and mirrors the reference's class and
+ * method names; INTEGRATION.md shows the stub a Sus-Net maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer argument is a DEVICE pointer on the env's device
+ *     unless the comment says "host";
+ *   - every call returns 0 on success or a negative SUS_ERR_* code; sus_last_error() returns the message
+ *     of the calling thread's last failure;
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*); no call synchronises the
+ *     device except sus_env_check_actions() and sus_env_create()/destroy();
+ *   - calls on one handle are not thread-safe (neither is the reference: it uses numpy's global RNG).
+ *
+ * Batch layout: env e of a handle has the global id env_id_base + e, which keys its Philox stream
+ * together with `seed` and the launch tick, so results do not depend on how envs are sharded over GPUs.
+ */
+#ifndef SUSNET_B200_H_
+#define SUSNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUS_ABI_VERSION 1
+
+#define SUS_MAX_AGENTS 8
+#define SUS_MAX_JOBS 8
+#define SUS_N_METRICS 8  /* per-episode counters, order of SusMetricIndex */
+#define SUS_N_STATS 10   /* finished-episode accumulators, order of SusStatIndex */
+#define SUS_MAX_FLAT_COMPONENTS 16
+
+enum SusError {
+  SUS_OK = 0,
+  SUS_ERR_INVALID_ARGUMENT = -1, /* reference: AssertionError from _validate_init_args / step asserts */
+  SUS_ERR_UNSUPPORTED = -2,      /* valid for the reference, outside this build's limits (A, J > 8 ...) */
+  SUS_ERR_CUDA = -3,
+  SUS_ERR_INVALID_ACTION = -4    /* reference: IndexError from agent_action_map[i][a] (base.py:381) */
+};
+
+/* src/environment/{base.py:102, tagging.py:9, pred_prey.py:20} */
+enum SusVariant { SUS_VARIANT_BASE = 0, SUS_VARIANT_TAGGING = 1, SUS_VARIANT_TRAINING_GROUND = 2 };
+
+enum SusDtype { SUS_U8 = 0, SUS_I32 = 1, SUS_I64 = 2, SUS_F32 = 3, SUS_F64 = 4 };
+
+/* src/metrics.py:7-32 -- the counters the env touches (base.py:366,508,522,531; tagging.py:199,201;
+ * base.py:433,444; pred_prey.py:90,96). */
+enum SusMetricIndex {
+  SUS_M_TOTAL_TIME_STEPS = 0, SUS_M_IMP_KILLED_CREW, SUS_M_COMPLETED_JOBS, SUS_M_SABOTAGED_JOBS,
+  SUS_M_IMP_VOTED_OUT, SUS_M_CREW_VOTED_OUT, SUS_M_CREW_WON, SUS_M_IMPOSTER_WON
+};
+
+/* Sums over FINISHED episodes (what EpisodicMetricHandler.step(info) receives at train.py:427). */
+enum SusStatIndex {
+  SUS_S_EPISODES = 0, SUS_S_CREW_WON, SUS_S_IMPOSTER_WON, SUS_S_IMP_KILLED_CREW, SUS_S_COMPLETED_JOBS,
+  SUS_S_SABOTAGED_JOBS, SUS_S_IMP_VOTED_OUT, SUS_S_CREW_VOTED_OUT, SUS_S_TOTAL_TIME_STEPS, SUS_S_TRUNCATED
+};
+
+/* Constructor arguments of FourRoomEnv (base.py:103-120), FourRoomEnvWithTagging (tagging.py:10-12) and
+ * ImposterTrainingGround (pred_prey.py:26-66; the host normalises its fixed arguments: n_imposters = 1,
+ * dead_penalty = 0, is_action_order_random = 0), plus the batch/sharding fields the reference has no
+ * analogue for. */
+typedef struct SusConfig {
+  int32_t variant;                /* SusVariant */
+  int32_t n_imposters;
+  int32_t n_crew;
+  int32_t n_jobs;
+  int32_t include_walls;          /* base.py:171-193 */
+  int32_t is_action_order_random; /* base.py:372-374 */
+  int32_t shuffle_imposter_index; /* base.py:273-278 */
+  int32_t max_time_steps;         /* base.py:118,392-395 */
+  int32_t tag_reset_interval;     /* tagging.py:11,184 */
+  int32_t auto_reset;             /* 1: a step that ends an episode resets the env in the same launch
+                                     (train.py:419-445 does this on the host) */
+  double kill_reward;             /* base.py:110 */
+  double complete_job_reward;
+  double sabotage_reward;
+  double time_step_reward;
+  double game_end_reward;
+  double dead_penalty;
+  double vote_reward;             /* tagging.py:11 */
+  int64_t num_envs;
+  uint64_t seed;                  /* Philox key */
+  uint32_t env_id_base;           /* global id of env 0 (sharding across GPUs) */
+  uint32_t reserved;
+} SusConfig;
+
+/* Observation encodings of src/features/model_ready.py. */
+enum SusEncodeKind {
+  SUS_ENCODE_NONE = 0,
+  SUS_ENCODE_GLOBAL = 1,      /* GlobalFeaturizer      model_ready.py:219-306 */
+  SUS_ENCODE_PERSPECTIVE = 2, /* PerspectiveFeaturizer model_ready.py:82-216  */
+  SUS_ENCODE_FLAT = 3         /* FlatFeaturizer over a CompositeFeaturizer, model_ready.py:309-367 */
+};
+
+/* Per-state featurizers of src/features/component.py usable inside SUS_ENCODE_FLAT. */
+enum SusFlatComponent {
+  SUS_FC_ONEHOT_POS = 0,       /* OneHotAgentPositionFeaturizer        component.py:221-247 */
+  SUS_FC_COORDS = 1,           /* CoordinateAgentPositionsFeaturizer   component.py:384-403 */
+  SUS_FC_ALIVE_CREW = 2,       /* AliveCrewFeaturizer                  component.py:406-425 */
+  SUS_FC_CLOSEST_CREW = 3,     /* ClosestAliveCrewFeaturizer           component.py:455-482 */
+  SUS_FC_L1_CREW = 4,          /* L1CrewFeaturizer                     component.py:428-452 */
+  SUS_FC_DIST_TO_IMPOSTER = 5, /* DistanceToImposterFeaturizer         component.py:250-278 */
+  SUS_FC_WALLS = 6,            /* WallsFeaturizer                      component.py:281-300 */
+  SUS_FC_ROOMS = 7,            /* ImposterVSCrewRoomLocaionFeaturizer  component.py:303-334 */
+  SUS_FC_SCENT = 8,            /* ImposterScentFeaturizer              component.py:339-380 */
+  SUS_FC_STATE_ALIVE = 9,      /* StateFieldFeaturizer(ALIVE_AGENTS)   component.py:200-218 */
+  SUS_FC_STATE_JOB_STATUS = 10,
+  SUS_FC_STATE_USED_TAGS = 11,
+  SUS_FC_STATE_TAG_COUNTS = 12,
+  SUS_FC_COUNT = 13
+};
+
+typedef struct SusEncodeSpec {
+  int32_t kind;         /* SusEncodeKind */
+  int32_t n_components; /* SUS_ENCODE_FLAT only */
+  int32_t components[SUS_MAX_FLAT_COMPONENTS];
+} SusEncodeSpec;
+
+/* Output shapes of an encode spec for a config (host call, no GPU work):
+ *   spatial_floats     per item per view: (A+2)*81 for GLOBAL/PERSPECTIVE, 0 for FLAT
+ *   non_spatial_floats per item per view: F
+ *   spatial_views      1 (GLOBAL: all views share the planes), A (PERSPECTIVE), 0 (FLAT)
+ *   non_spatial_views  A (GLOBAL, PERSPECTIVE), 1 (FLAT: every view is identical)
+ * Replaces SequenceStateFeaturizer.featurized_shape (model_ready.py:115-123,249-253,318-323). */
+typedef struct SusEncodeShape {
+  int32_t spatial_floats, non_spatial_floats, spatial_views, non_spatial_views;
+} SusEncodeShape;
+
+/* Inputs and outputs of one step launch.  NULL output pointers are skipped. */
+typedef struct SusStepIO {
+  const void *actions;     /* [N][A] role-list indices (base.py:381); NULL = fused random policy, i.e.
+                              env.step(env.sample_actions()) with the SUS_P_ACT_FUSED draws */
+  int32_t actions_dtype;   /* SUS_U8 / SUS_I32 / SUS_I64 */
+  int32_t rewards_dtype;   /* SUS_F32 (replay layout, replay_memory.py:38) or SUS_F64 (numpy step result) */
+  void *rewards;           /* [N][A] */
+  uint8_t *done;           /* [N] base.py:404 */
+  uint8_t *truncated;      /* [N] base.py:405 */
+  int32_t *actions_out;    /* [N][A] the actions applied (useful with the random policy) */
+  float *next_flat;        /* [N][S] post-step, PRE-reset state in flatten order = the row the reference
+                              stores in next_states[:, -1] (train.py:388-399, replay_memory.py:120-126) */
+  int64_t *metrics;        /* [N][SUS_N_METRICS] pre-reset episode counters = the step's `info` dict */
+  const SusEncodeSpec *encode; /* host pointer or NULL: fused encode of the state the NEXT action is
+                              taken from (post auto-reset), written to spatial / non_spatial below */
+  float *spatial;          /* [views_s][N][spatial_floats]  */
+  float *non_spatial;      /* [views_n][N][non_spatial_floats] */
+} SusStepIO;
+
+typedef struct SusEnv *sus_env_t;
+
+int sus_abi_version(void);
+const char *sus_last_error(void); /* host string, valid until the thread's next failing call */
+
+/* S = env.flattened_state_size (base.py:230-232); n_actions: env.n_imposter_actions / n_crew_actions
+ * (base.py:203-204, tagging.py:35-36, pred_prey.py:69-73).  Host calls. */
+int sus_flat_state_size(const SusConfig *cfg);
+int sus_n_role_actions(const SusConfig *cfg, int is_imposter);
+int sus_encode_shape(const SusConfig *cfg, const SusEncodeSpec *spec, SusEncodeShape *out /*host*/);
+
+/* FourRoomEnv.__init__ & co. (base.py:103-228): validates like _validate_init_args (base.py:243-249,
+ * pred_prey.py:75-76), builds the wall grid, allocates the structure-of-arrays state for num_envs envs on
+ * `device`.  The envs are NOT reset. */
+int sus_env_create(const SusConfig *cfg, int device, sus_env_t *out /*host*/);
+int sus_env_destroy(sus_env_t env);
+
+/* FourRoomEnv.reset (base.py:251-324; tagging.py:62-101) for every env whose mask byte is non-zero
+ * (all envs if mask is NULL).  Kernel K0. */
+int sus_env_reset(sus_env_t env, const uint8_t *mask_or_null, void *stream);
+
+/* FourRoomEnv.step (base.py:332-407), FourRoomEnvWithTagging.step (tagging.py:120-235),
+ * ImposterTrainingGround.check_win_condition (pred_prey.py:78-99), with auto-reset and the optional fused
+ * observation encode.  Kernel K1 (+K2 fused).  Invalid role-list indices do not abort the launch: the env's
+ * step is skipped and a device-side error counter is raised (see sus_env_check_actions). */
+int sus_env_step(sus_env_t env, const SusStepIO *io /*host*/, void *stream);
+
+/* Synchronises `stream` and returns SUS_ERR_INVALID_ACTION if any step since the last check saw an action
+ * index outside its agent's role list (reference: IndexError, base.py:381), else 0. */
+int sus_env_check_actions(sus_env_t env, void *stream);
+
+/* FourRoomEnv.sample_actions (base.py:326-330): uniform over each agent's role-specific list, dead agents
+ * included.  Kernel K3.  out: [N][A] int32. */
+int sus_env_sample_actions(sus_env_t env, int32_t *out, void *stream);
+
+/* env.flatten_state(current state) (base.py:234-235) for all envs; dtype SUS_F32 / SUS_F64 / SUS_I64. */
+int sus_env_export_flat(sus_env_t env, int32_t dtype, void *out /*[N][S]*/, void *stream);
+/* Load states from flatten-order rows (inverse of the above) plus role masks and time steps. */
+int sus_env_import_flat(sus_env_t env, const int64_t *flat /*[N][S]*/, const uint8_t *imposter_mask /*[N][A]*/,
+                        const int32_t *t_or_null /*[N]*/, void *stream);
+/* env.imposter_mask (base.py:280-281) as [N][A] bytes; env.imposter_idxs is its ascending index list. */
+int sus_env_export_imposter_mask(sus_env_t env, uint8_t *out, void *stream);
+/* env.metrics.get_metrics() (metrics.py:60-61) for all envs: [N][SUS_N_METRICS] int64. */
+int sus_env_export_metrics(sus_env_t env, int64_t *out, void *stream);
+
+/* SequenceStateFeaturizer.fit + generate_featurized_states on the envs' CURRENT states, T = 1.  Kernel K2. */
+int sus_env_encode(sus_env_t env, const SusEncodeSpec *spec /*host*/, float *spatial, float *non_spatial,
+                   void *stream);
+/* SequenceStateFeaturizer.fit on a (B, T, S) batch of flattened states (train.py:70-74,346-348):
+ * n_items = B*T rows of S values, dtype SUS_F32 / SUS_F64 / SUS_I64 (floats are truncated like
+ * gymnasium.spaces.unflatten does).  Output item order = row order, so (B,T,...) views are free. */
+int sus_encode_from_flat(const SusConfig *cfg /*host*/, const SusEncodeSpec *spec /*host*/, const void *states,
+                         int32_t dtype, int64_t n_items, float *spatial, float *non_spatial, int device,
+                         void *stream);
+
+/* Finished-episode accumulators (SusStatIndex) of this handle since creation (or the last clear), int64[10].
+ * These are what the multi-GPU driver all-reduces with NCCL at the end of a run. */
+int sus_env_stats(sus_env_t env, int64_t *out, void *stream);
+int sus_env_clear_stats(sus_env_t env, void *stream);
+
+/* Launch ticks of the three Philox streams (host values), for checkpoint/resume. */
+int sus_env_get_ticks(sus_env_t env, uint64_t *step_tick, uint64_t *reset_epoch, uint64_t *act_epoch /*host*/);
+int sus_env_set_ticks(sus_env_t env, uint64_t step_tick, uint64_t reset_epoch, uint64_t act_epoch);
+
+/* Raw structure-of-arrays state (device pointers, bytes per env) for state_dict()/load_state_dict(). */
+int sus_env_state_arrays(sus_env_t env, void **ptrs /*host [4]*/, int32_t *bytes_per_env /*host [4]*/);
+
+/* Parity mode: raw 32-bit words that replace the Philox output of the NEXT launch that draws from the
+ * stream (step_words [N][2A-1], reset_words [N][n_imp+A+J], act_words [N][A]); NULL leaves a stream alone. */
+int sus_env_debug_inject_words(sus_env_t env, const uint32_t *step_words, const uint32_t *reset_words,
+                               const uint32_t *act_words);
+
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t sus_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUSNET_B200_H_ */

@@ -1,0 +1,263 @@
+"""TEST INFRASTRUCTURE (oracle/) -- never imported by the product path.
+
+Runs the UNMODIFIED Sus-Net reference (`/root/reference/src`, imported through the
+gymnasium stand-in in `tests/_shims`) on *injected* random draws, so the C oracle
+and the CUDA kernels can be compared with the real thing bit for bit.
+
+The reference draws from numpy's global RNG at six call sites (SURVEY.md A.6,
+`src/environment/base.py:274,288,295,329,374,497`, `tagging.py:167`).
+`np.random.choice` / `np.random.shuffle` are looked up at call time, so assigning
+wrappers on the module replaces them without touching the reference.  The wrappers
+discriminate the call sites by signature and answer with the semantic draw derived
+from the susnet Philox spec (`oracle/rng_spec.py`).
+
+Only usable where `/root/reference` exists (the build container).  The GPU box never
+imports this module: golden fixtures made with it live in `tests/golden/`.
+"""
+import os
+import sys
+
+import numpy as np
+
+from . import rng_spec as R
+
+REFERENCE_ROOT = os.environ.get("SUSNET_REFERENCE_ROOT", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "_shims")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "environment"))
+
+
+def import_reference():
+    """Put the shims + reference on sys.path and return (env module, features module)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    for p in (_SHIMS, os.path.join(_SHIMS, "stubs"), REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import src.environment as env_mod  # noqa: E402
+    import src.features as feat_mod  # noqa: E402
+
+    return env_mod, feat_mod
+
+
+class DrawContext:
+    """What the patched numpy functions answer with for the env currently being driven."""
+
+    def __init__(self):
+        self.active = False
+        self.cfg = None
+        self.step_words = None
+        self.reset_words = None
+        self.act_words = None
+        self.kill_events = 0
+        self.act_calls = 0
+
+
+_CTX = DrawContext()
+_ORIG = {}
+
+
+def _choice(a, size=None, replace=True, p=None):
+    c = _CTX
+    if not c.active:
+        return _ORIG["choice"](a, size=size, replace=replace, p=p)
+    cfg = c.cfg
+    A, n_imp, J, V = cfg["n_agents"], cfg["n_imposters"], cfg["n_jobs"], cfg["n_valid"]
+    if isinstance(a, range):  # R1: imposter ids
+        assert size == n_imp and replace is False
+        imps = sorted(R.pick_distinct(c.reset_words[:n_imp], A))
+        return np.array(imps, dtype=np.int64)
+    if isinstance(a, (int, np.integer)) and size is not None and replace is True:  # R2: spawn cells
+        assert int(a) == V and size == A
+        return np.array([R.bounded(c.reset_words[n_imp + i], V) for i in range(A)], dtype=np.int64)
+    if isinstance(a, (int, np.integer)) and size is not None and replace is False:  # R3: job cells
+        assert int(a) == V and size == J
+        base = n_imp + A
+        return np.array(R.pick_distinct(c.reset_words[base : base + J], V), dtype=np.int64)
+    if isinstance(a, list):  # R5: victim
+        assert size is None and len(a) >= 1
+        w = c.step_words[A - 1 + c.kill_events]
+        c.kill_events += 1
+        return a[R.bounded(w, len(a))]
+    if isinstance(a, (int, np.integer)) and size is None:  # R6: random action
+        w = c.act_words[c.act_calls]
+        c.act_calls += 1
+        return R.bounded(w, int(a))
+    raise AssertionError(f"unexpected np.random.choice call: {a!r}, size={size}, replace={replace}")
+
+
+def _shuffle(x):
+    c = _CTX
+    if not c.active:
+        return _ORIG["shuffle"](x)
+    A = c.cfg["n_agents"]
+    assert isinstance(x, list) and len(x) == A  # R4
+    x[:] = R.action_order(c.step_words, A)
+
+
+def install():
+    if "choice" not in _ORIG:
+        _ORIG["choice"] = np.random.choice
+        _ORIG["shuffle"] = np.random.shuffle
+    np.random.choice = _choice
+    np.random.shuffle = _shuffle
+
+
+def uninstall():
+    if "choice" in _ORIG:
+        np.random.choice = _ORIG["choice"]
+        np.random.shuffle = _ORIG["shuffle"]
+
+
+VARIANTS = ("base", "tagging", "training_ground")
+
+
+def make_reference_env(cfg):
+    """cfg: dict in the susnet-b200 config vocabulary (see sus_net_b200.config.EnvConfig)."""
+    env_mod, _ = import_reference()
+    v = cfg["variant"]
+    if v == "training_ground":
+        return env_mod.ImposterTrainingGround(
+            n_crew=cfg["n_crew"],
+            n_jobs=cfg["n_jobs"],
+            time_step_reward=cfg["time_step_reward"],
+            kill_reward=cfg["kill_reward"],
+            sabotage_reward=cfg["sabotage_reward"],
+            end_of_game_reward=cfg["game_end_reward"],
+            shuffle_imposter_index=cfg["shuffle_imposter_index"],
+            include_walls=cfg["include_walls"],
+        )
+    kw = dict(
+        n_imposters=cfg["n_imposters"],
+        n_crew=cfg["n_crew"],
+        n_jobs=cfg["n_jobs"],
+        is_action_order_random=cfg["is_action_order_random"],
+        kill_reward=cfg["kill_reward"],
+        complete_job_reward=cfg["complete_job_reward"],
+        sabotage_reward=cfg["sabotage_reward"],
+        time_step_reward=cfg["time_step_reward"],
+        game_end_reward=cfg["game_end_reward"],
+        dead_penalty=cfg["dead_penalty"],
+        shuffle_imposter_index=cfg["shuffle_imposter_index"],
+        max_time_steps=cfg["max_time_steps"],
+        include_walls=cfg["include_walls"],
+    )
+    if v == "tagging":
+        return env_mod.FourRoomEnvWithTagging(
+            **kw, tag_reset_interval=cfg["tag_reset_interval"], vote_reward=cfg["vote_reward"]
+        )
+    assert v == "base"
+    return env_mod.FourRoomEnv(**kw)
+
+
+METRIC_KEYS = (
+    "total_time_steps",
+    "imp_killed_crew",
+    "completed_jobs",
+    "sabotaged_jobs",
+    "imp_voted_out",
+    "crew_voted_out",
+    "crew_won",
+    "imposter_won",
+)
+
+
+class ReferenceBatch:
+    """N independent reference envs driven in lock step with the batched auto-reset contract
+    (SURVEY.md A.7): a step that ends an episode reports the terminal state, then the env is
+    reset with the AUTORESET draws of the same tick."""
+
+    def __init__(self, cfg, num_envs, seed, env_id_base=0, auto_reset=True):
+        self.cfg = dict(cfg)
+        self.N = num_envs
+        self.seed = seed
+        self.env_ids = np.arange(env_id_base, env_id_base + num_envs, dtype=np.uint64)
+        self.auto_reset = auto_reset
+        install()
+        self.envs = [make_reference_env(self.cfg) for _ in range(num_envs)]
+        e0 = self.envs[0]
+        self.cfg["n_agents"] = e0.n_agents
+        self.cfg["n_imposters"] = e0.n_imposters
+        self.cfg["n_valid"] = len(e0.valid_positions)
+        self.A, self.J = e0.n_agents, e0.n_jobs
+        self.step_tick = 0
+        self.reset_epoch = 0
+        self.act_epoch = 0
+        self.states = [None] * num_envs
+        self.S = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _flat(self, i):
+        return np.asarray(self.envs[i].flatten_state(self.states[i]), dtype=np.int64)
+
+    def _metrics(self, i):
+        m = self.envs[i].metrics.metrics
+        return np.array([int(m[k]) for k in METRIC_KEYS], dtype=np.int64)
+
+    def _reset_one(self, i, words):
+        _CTX.active, _CTX.cfg, _CTX.reset_words = True, self.cfg, words
+        try:
+            s, _ = self.envs[i].reset()
+        finally:
+            _CTX.active = False
+        self.states[i] = s
+
+    # -- API -------------------------------------------------------------------------------
+    def reset(self):
+        w = R.words(self.seed, self.env_ids, self.reset_epoch, R.P_RESET,
+                    R.n_reset_slots(self.cfg["n_imposters"], self.A, self.J))
+        self.reset_epoch += 1
+        for i in range(self.N):
+            self._reset_one(i, w[i])
+        return self.flat_states()
+
+    def flat_states(self):
+        return np.stack([self._flat(i) for i in range(self.N)])
+
+    def imposter_idxs(self):
+        return np.stack([np.asarray(e.imposter_idxs, dtype=np.int64) for e in self.envs])
+
+    def sample_actions(self):
+        w = R.words(self.seed, self.env_ids, self.act_epoch, R.P_ACT, self.A)
+        self.act_epoch += 1
+        out = np.zeros((self.N, self.A), dtype=np.int64)
+        for i in range(self.N):
+            _CTX.active, _CTX.cfg, _CTX.act_words, _CTX.act_calls = True, self.cfg, w[i], 0
+            try:
+                out[i] = self.envs[i].sample_actions()
+            finally:
+                _CTX.active = False
+        return out
+
+    def step(self, actions):
+        """actions (N, A) ints -> dict of next_flat (pre-reset), rewards f64, done, trunc, metrics (pre-reset)."""
+        A = self.A
+        ws = R.words(self.seed, self.env_ids, self.step_tick, R.P_STEP, R.n_step_slots(A))
+        wr = R.words(self.seed, self.env_ids, self.step_tick, R.P_AUTORESET,
+                     R.n_reset_slots(self.cfg["n_imposters"], A, self.J))
+        self.step_tick += 1
+        S = self.envs[0].flattened_state_size
+        out = dict(
+            next_flat=np.zeros((self.N, S), dtype=np.int64),
+            rewards=np.zeros((self.N, A), dtype=np.float64),
+            done=np.zeros(self.N, dtype=np.uint8),
+            trunc=np.zeros(self.N, dtype=np.uint8),
+            metrics=np.zeros((self.N, len(METRIC_KEYS)), dtype=np.int64),
+        )
+        for i in range(self.N):
+            _CTX.active, _CTX.cfg, _CTX.step_words, _CTX.kill_events = True, self.cfg, ws[i], 0
+            try:
+                s, r, d, t, _info = self.envs[i].step(np.asarray(actions[i]))
+            finally:
+                _CTX.active = False
+            self.states[i] = s
+            out["next_flat"][i] = self._flat(i)
+            out["rewards"][i] = r
+            out["done"][i] = d
+            out["trunc"][i] = t
+            out["metrics"][i] = self._metrics(i)
+            if self.auto_reset and (d or t):
+                self._reset_one(i, wr[i])
+        return out

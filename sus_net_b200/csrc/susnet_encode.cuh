@@ -1,0 +1,212 @@
+// susnet_encode.cuh -- observation featurizers (src/features/component.py, model_ready.py) on the GPU.
+//
+// Output tensors (float32, item-major so that (B, T, ...) views of B*T items are free):
+//   GLOBAL       spatial [n][A+2][9][9] (one copy, shared by all agent views)   non_spatial [A][n][F]
+//   PERSPECTIVE  spatial [A][n][A+2][9][9]                                      non_spatial [A][n][F]
+//   FLAT         (no spatial tensor; the reference returns zeros(B,T,1))        non_spatial [n][F]
+// Plane index order is [channel][x][y] (component.py:47-49,98,125).
+#pragma once
+#include "susnet_device.cuh"
+
+namespace susnet {
+
+struct DevEncode {
+  int32_t kind, n_components, sp_floats, ns_floats;
+  int32_t components[SUS_MAX_FLAT_COMPONENTS];
+};
+
+// Zero `n_floats` floats starting at `base` with the whole warp: scalar stores up to the first 16-byte
+// boundary, 128-bit stores over the aligned body, scalar stores over the (at most 3-float) tail.
+__device__ __forceinline__ void warp_zero_fill(float* __restrict__ base, int64_t n_floats, int lane) {
+  int64_t head = (int64_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(base) & 15u)) & 15u) >> 2;
+  if (head > n_floats) head = n_floats;
+  if (lane < head) base[lane] = 0.f;
+  float* body = base + head;
+  const int64_t n = n_floats - head, n4 = n >> 2;
+  float4* b4 = reinterpret_cast<float4*>(body);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int64_t i = lane; i < n4; i += 32) b4[i] = z;
+  const int64_t tail = (n4 << 2) + lane;
+  if (tail < n) body[tail] = 0.f;
+}
+
+__device__ __forceinline__ bool code_ok(uint32_t c) { return (c >> 4) <= 8u && (c & 15u) <= 8u; }
+
+// agent / job planes of one item; `ch_of(i)` gives the channel agent i is shown in
+// (AgentPositionsFeaturizer component.py:90-100, JobFeaturizer component.py:116-127).
+template <typename ChannelOf>
+__device__ __forceinline__ void scatter_planes(const DevConfig& c, const ObsState& o, float* __restrict__ sp,
+                                               ChannelOf ch_of) {
+  const int A = c.A, J = c.J;
+  for (int i = 0; i < A; ++i) {
+    const uint32_t b = get_byte(o.pos, i);
+    if (((o.alive >> i) & 1u) && code_ok(b)) sp[ch_of(i) * 81 + code_cell(b)] = 1.0f;
+  }
+  for (int j = 0; j < J; ++j) {
+    const uint32_t b = get_byte(o.jobpos, j);
+    if (code_ok(b)) sp[(A + (int)((o.jobdone >> j) & 1u)) * 81 + code_cell(b)] = 1.0f;
+  }
+}
+
+// GlobalFeaturizer non-spatial row of view k: alive, [tag counts], job status, one-hot(k)
+// (model_ready.py:237-247,293-303).  Tagging fields are read in TUPLE order (documented deviation from
+// the reference's inconsistent state_fields map).
+__device__ __forceinline__ void global_ns_row(const DevConfig& c, const ObsState& o, int k, float* __restrict__ r) {
+  const int A = c.A, J = c.J;
+  int p = 0;
+  for (int i = 0; i < A; ++i) r[p++] = (float)((o.alive >> i) & 1u);
+  if (c.variant == SUS_VARIANT_TAGGING)
+    for (int i = 0; i < A; ++i) r[p++] = (float)((o.tagcnt >> (4 * i)) & 15u);
+  for (int j = 0; j < J; ++j) r[p++] = (float)((o.jobdone >> j) & 1u);
+  for (int i = 0; i < A; ++i) r[p++] = i == k ? 1.0f : 0.0f;
+}
+
+// PerspectiveFeaturizer: view k shows agents in the order [k, 0..k-1, k+1..A-1] (model_ready.py:184-193)
+__device__ __forceinline__ int persp_agent_of_channel(int k, int ch) { return ch == 0 ? k : (ch <= k ? ch - 1 : ch); }
+__device__ __forceinline__ int persp_channel_of_agent(int k, int i) { return i == k ? 0 : (i < k ? i + 1 : i); }
+
+__device__ __forceinline__ void persp_ns_row(const DevConfig& c, const ObsState& o, int k, float* __restrict__ r) {
+  const int A = c.A, J = c.J;
+  int p = 0;  // per-agent fields, field-major, permuted like the channels; then job status (model_ready.py:195-204)
+  for (int ch = 0; ch < A; ++ch) r[p++] = (float)((o.alive >> persp_agent_of_channel(k, ch)) & 1u);
+  if (c.variant == SUS_VARIANT_TAGGING)
+    for (int ch = 0; ch < A; ++ch) r[p++] = (float)((o.tagcnt >> (4 * persp_agent_of_channel(k, ch))) & 15u);
+  for (int j = 0; j < J; ++j) r[p++] = (float)((o.jobdone >> j) & 1u);
+}
+
+__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
+
+// One component of a CompositeFeaturizer (component.py); returns the number of floats written.
+__device__ __forceinline__ int flat_component(const DevConfig& c, const GridTables& tb, const ObsState& o, int comp,
+                                              float* __restrict__ r) {
+  const int A = c.A, J = c.J;
+  const uint32_t b0 = get_byte(o.pos, 0);  // "imposter is agent 0" (component.py:262,289,355,440,467)
+  const int ix = (int)code_x(b0), iy = (int)code_y(b0);
+  int p = 0;
+  switch (comp) {
+    case SUS_FC_ONEHOT_POS:  // component.py:226-240
+      for (int i = 0; i < A; ++i) {
+        const uint32_t b = get_byte(o.pos, i);
+        const bool al = (o.alive >> i) & 1u;
+        for (int q = 0; q < 9; ++q) r[p++] = (al && code_x(b) == (uint32_t)q) ? 1.0f : 0.0f;
+        for (int q = 0; q < 9; ++q) r[p++] = (al && code_y(b) == (uint32_t)q) ? 1.0f : 0.0f;
+      }
+      break;
+    case SUS_FC_COORDS:  // component.py:389-399 (dead agents included)
+      for (int i = 0; i < A; ++i) {
+        const uint32_t b = get_byte(o.pos, i);
+        r[p++] = (float)code_x(b); r[p++] = (float)code_y(b);
+      }
+      break;
+    case SUS_FC_ALIVE_CREW:  // component.py:411-421
+      for (int i = 1; i < A; ++i) r[p++] = (float)((o.alive >> i) & 1u);
+      break;
+    case SUS_FC_CLOSEST_CREW: {  // component.py:460-478: default distance 18, first argmin
+      int best = 0, best_d = 1 << 20;
+      for (int i = 1; i < A; ++i) {
+        const uint32_t b = get_byte(o.pos, i);
+        const int d = ((o.alive >> i) & 1u) ? iabs(ix - (int)code_x(b)) + iabs(iy - (int)code_y(b)) : 18;
+        if (d < best_d) { best_d = d; best = i - 1; }
+      }
+      for (int i = 0; i < A - 1; ++i) r[p++] = i == best ? 1.0f : 0.0f;
+    } break;
+    case SUS_FC_L1_CREW:  // component.py:433-448
+      for (int i = 1; i < A; ++i) {
+        const uint32_t b = get_byte(o.pos, i);
+        r[p++] = ((o.alive >> i) & 1u) ? (float)(iabs(ix - (int)code_x(b)) + iabs(iy - (int)code_y(b))) : -1.0f;
+      }
+      break;
+    case SUS_FC_DIST_TO_IMPOSTER: {  // component.py:255-273: alive others compacted, trailing zeros
+      const int n = 2 * (A - 1);
+      for (int i = 1; i < A; ++i) {
+        const uint32_t b = get_byte(o.pos, i);
+        if ((o.alive >> i) & 1u) { r[p++] = (float)(ix - (int)code_x(b)); r[p++] = (float)(iy - (int)code_y(b)); }
+      }
+      while (p < n) r[p++] = 0.0f;
+    } break;
+    case SUS_FC_WALLS:  // component.py:286-296: 3x3 patch of the zero-padded grid around agent 0
+      for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy) {
+          const uint32_t nb = ((uint32_t)(ix + dx) << 4 | ((uint32_t)(iy + dy) & 15u)) & 0xffu;
+          const bool in = (uint32_t)(ix + dx) <= 8u && (uint32_t)(iy + dy) <= 8u;
+          r[p++] = (in && ((tb.valid_bits[nb >> 5] >> (nb & 31u)) & 1u)) ? 1.0f : 0.0f;
+        }
+      break;
+    case SUS_FC_ROOMS: {  // component.py:308-329, ROOM_MASKS component.py:8-17
+      int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int i = 0; i < A; ++i) {
+        if (!((o.alive >> i) & 1u)) continue;
+        const uint32_t b = get_byte(o.pos, i);
+        const bool xl = code_x(b) < 5u, yl = code_y(b) < 5u;
+        const int room = xl ? (yl ? 0 : 1) : (yl ? 3 : 2);
+        const int at = (i == 0 ? 0 : 4) + room;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cnt[q] += q == at ? 1 : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) r[p++] = (float)cnt[q];
+    } break;
+    case SUS_FC_SCENT: {  // component.py:344-375: float32 accumulation of (9 - d) / 9 computed in double
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int i = 1; i < A; ++i) {
+        if (!((o.alive >> i) & 1u)) continue;
+        const uint32_t b = get_byte(o.pos, i);
+        const double xs = (9.0 - (double)((int)code_x(b) - ix)) / 9.0, ys = (9.0 - (double)((int)code_y(b) - iy)) / 9.0;
+        if (xs > 0) s0 += (float)xs; else s1 += (float)xs;
+        if (ys > 0) s2 += (float)ys; else s3 += (float)ys;
+      }
+      r[p++] = s0; r[p++] = s1; r[p++] = s2; r[p++] = s3;
+    } break;
+    case SUS_FC_STATE_ALIVE:  // StateFieldFeaturizer: component.py:210-214
+      for (int i = 0; i < A; ++i) r[p++] = (float)((o.alive >> i) & 1u);
+      break;
+    case SUS_FC_STATE_JOB_STATUS:
+      for (int j = 0; j < J; ++j) r[p++] = (float)((o.jobdone >> j) & 1u);
+      break;
+    case SUS_FC_STATE_USED_TAGS:
+      for (int i = 0; i < A; ++i) r[p++] = (float)((o.used >> i) & 1u);
+      break;
+    case SUS_FC_STATE_TAG_COUNTS:
+      for (int i = 0; i < A; ++i) r[p++] = (float)((o.tagcnt >> (4 * i)) & 15u);
+      break;
+  }
+  return p;
+}
+
+// Encode the 32 items a warp owns (item = item0 + lane; `cnt` of them exist, `have` says whether this
+// lane's item exists).  All 32 lanes must call this together.
+__device__ __forceinline__ void warp_encode(const DevConfig& c, const DevEncode& enc, const GridTables& tb,
+                                            const ObsState& o, int64_t item0, int cnt, bool have, int64_t n_items,
+                                            float* __restrict__ spatial, float* __restrict__ non_spatial) {
+  const int lane = threadIdx.x & 31;
+  const int64_t item = item0 + lane;
+  const int A = c.A;
+  if (enc.kind == SUS_ENCODE_GLOBAL) {
+    const int R = enc.sp_floats;
+    warp_zero_fill(spatial + item0 * R, (int64_t)cnt * R, lane);
+    __syncwarp();
+    if (have) {
+      scatter_planes(c, o, spatial + item * R, [](int i) { return i; });
+      for (int k = 0; k < A; ++k) global_ns_row(c, o, k, non_spatial + ((int64_t)k * n_items + item) * enc.ns_floats);
+    }
+  } else if (enc.kind == SUS_ENCODE_PERSPECTIVE) {
+    const int R = enc.sp_floats;
+    for (int k = 0; k < A; ++k) warp_zero_fill(spatial + ((int64_t)k * n_items + item0) * R, (int64_t)cnt * R, lane);
+    __syncwarp();
+    if (have) {
+      for (int k = 0; k < A; ++k) {
+        scatter_planes(c, o, spatial + ((int64_t)k * n_items + item) * R,
+                       [k](int i) { return persp_channel_of_agent(k, i); });
+        persp_ns_row(c, o, k, non_spatial + ((int64_t)k * n_items + item) * enc.ns_floats);
+      }
+    }
+  } else if (enc.kind == SUS_ENCODE_FLAT) {
+    if (have) {
+      float* r = non_spatial + item * enc.ns_floats;
+      for (int q = 0; q < enc.n_components; ++q) r += flat_component(c, tb, o, enc.components[q], r);
+    }
+  }
+}
+
+}  // namespace susnet

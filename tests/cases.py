@@ -1,0 +1,42 @@
+"""Canonical env configurations (BASELINE.json `configs`) plus edge cases, shared by the
+golden generator and the parity tests."""
+from oracle import default_config
+
+CASES = {
+    # cfg1: ImposterTrainingGround 1v1, empty grid (notebooks/experiment_1v1.ipynb "No Wall")
+    "cfg1_itg_1v1_nowall": default_config("training_ground", n_crew=1, n_jobs=0, kill_reward=-3.0, sabotage_reward=0.0,
+                                          game_end_reward=0.0, time_step_reward=0.0, include_walls=False),
+    # cfg2: same, walled grid
+    "cfg2_itg_1v1_wall": default_config("training_ground", n_crew=1, n_jobs=0, kill_reward=-3.0, sabotage_reward=0.0,
+                                        game_end_reward=0.0, time_step_reward=0.0),
+    # cfg3: tagging 1v2, 5 jobs, all defaults
+    "cfg3_tagging_1v2": default_config("tagging", n_crew=2, n_jobs=5),
+    # cfg4 (headline): FourRoomEnv 1v4, 5 jobs, all defaults
+    "cfg4_base_1v4": default_config("base", n_crew=4, n_jobs=5),
+    # cfg4-alt: ImposterTrainingGround 1v4 walled
+    "cfg4alt_itg_1v4": default_config("training_ground", n_crew=4, n_jobs=0, kill_reward=-3.0, sabotage_reward=0.0,
+                                      game_end_reward=0.0, time_step_reward=0.0),
+    # edge cases
+    "base_2v3_j3": default_config("base", n_imposters=2, n_crew=3, n_jobs=3, max_time_steps=60),
+    "base_1v2_j0": default_config("base", n_crew=2, n_jobs=0),  # crew wins on step 1 (quirk C-4)
+    "base_fixed_order_tsr": default_config("base", n_crew=3, n_jobs=2, is_action_order_random=False,
+                                           shuffle_imposter_index=False, time_step_reward=-1.0, max_time_steps=40),
+    "tagging_2v5_short": default_config("tagging", n_imposters=2, n_crew=5, n_jobs=4, tag_reset_interval=7,
+                                        max_time_steps=50, time_step_reward=-1.0),
+    "tagging_1v4": default_config("tagging", n_crew=4, n_jobs=5),
+    "itg_1v3_jobs_shuffle": default_config("training_ground", n_crew=3, n_jobs=2, kill_reward=-3.0,
+                                           sabotage_reward=0.0, game_end_reward=5.0, time_step_reward=-0.5,
+                                           shuffle_imposter_index=True),
+    "base_1v7_j8_nowall": default_config("base", n_crew=7, n_jobs=8, include_walls=False, max_time_steps=30),
+}
+
+# featurizer coverage per case: which model-ready featurizers are defined for it
+GLOBAL_CASES = ["cfg4_base_1v4", "base_2v3_j3", "base_fixed_order_tsr", "base_1v7_j8_nowall", "itg_1v3_jobs_shuffle"]
+FLAT_COMPONENT_SETS = {
+    "cfg4alt_itg_1v4": [["onehot_pos", "alive_crew", "closest_crew"],
+                        ["coords", "l1_crew", "dist_to_imposter", "walls", "rooms", "scent", "state_alive"]],
+    "cfg2_itg_1v1_wall": [["onehot_pos"], ["coords"]],
+    "cfg1_itg_1v1_nowall": [["onehot_pos"], ["walls", "rooms"]],
+    "cfg4_base_1v4": [["onehot_pos", "state_alive", "state_job_status", "walls", "rooms", "l1_crew", "closest_crew",
+                       "dist_to_imposter", "scent", "coords", "alive_crew"]],
+}
