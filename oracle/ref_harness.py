@@ -205,9 +205,12 @@ class ReferenceBatch:
         self.states[i] = s
 
     # -- API -------------------------------------------------------------------------------
-    def reset(self):
+    def reset(self, reset_words=None):
+        """reset_words: optional (N, n_imp+A+J) raw words replacing the Philox stream (parity mode)."""
         w = R.words(self.seed, self.env_ids, self.reset_epoch, R.P_RESET,
                     R.n_reset_slots(self.cfg["n_imposters"], self.A, self.J))
+        if reset_words is not None:
+            w = np.asarray(reset_words, dtype=np.uint32)
         self.reset_epoch += 1
         for i in range(self.N):
             self._reset_one(i, w[i])
@@ -219,8 +222,10 @@ class ReferenceBatch:
     def imposter_idxs(self):
         return np.stack([np.asarray(e.imposter_idxs, dtype=np.int64) for e in self.envs])
 
-    def sample_actions(self):
+    def sample_actions(self, act_words=None):
         w = R.words(self.seed, self.env_ids, self.act_epoch, R.P_ACT, self.A)
+        if act_words is not None:
+            w = np.asarray(act_words, dtype=np.uint32)
         self.act_epoch += 1
         out = np.zeros((self.N, self.A), dtype=np.int64)
         for i in range(self.N):
@@ -231,12 +236,16 @@ class ReferenceBatch:
                 _CTX.active = False
         return out
 
-    def step(self, actions):
+    def step(self, actions, step_words=None, reset_words=None):
         """actions (N, A) ints -> dict of next_flat (pre-reset), rewards f64, done, trunc, metrics (pre-reset)."""
         A = self.A
         ws = R.words(self.seed, self.env_ids, self.step_tick, R.P_STEP, R.n_step_slots(A))
         wr = R.words(self.seed, self.env_ids, self.step_tick, R.P_AUTORESET,
                      R.n_reset_slots(self.cfg["n_imposters"], A, self.J))
+        if step_words is not None:
+            ws = np.asarray(step_words, dtype=np.uint32)
+        if reset_words is not None:
+            wr = np.asarray(reset_words, dtype=np.uint32)
         self.step_tick += 1
         S = self.envs[0].flattened_state_size
         out = dict(

@@ -1,0 +1,754 @@
+// susnet_api.cu -- kernels and C ABI (include/susnet_b200.h) of the B200-native Sus-Net simulator.
+//
+// Kernels (all sm_100a, one thread per env / item, 256-thread CTAs, wall grid staged in shared memory):
+//   K0 k_reset           FourRoomEnv.reset for a masked subset of envs
+//   K1 k_step<V, ENC>    fused step: action decode, ordered per-agent loop (move with wall collision, kill,
+//                        fix, sabotage, tag), vote tally, win / reward / done / truncation, episode-stat
+//                        flush, auto-reset, and (ENC) the observation encode of the state the next action
+//                        is taken from
+//   K2 k_encode_env / k_encode_rows<T>   featurizers on live env state / on (B*T, S) flattened rows
+//   K3 k_sample_actions  role-aware uniform random actions
+//   plus small export / import kernels for the reference's flatten order.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "susnet_device.cuh"
+#include "susnet_encode.cuh"
+
+using namespace susnet;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define SUS_CUDA(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) return fail(SUS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    else if (prev == dev) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------ params
+struct StepParams {
+  DevConfig c;
+  DevEncode enc;
+  StateArrays st;
+  const void* actions;
+  void* rewards;
+  uint8_t* done;
+  uint8_t* trunc;
+  int32_t* actions_out;
+  float* next_flat;
+  long long* metrics;
+  float* spatial;
+  float* non_spatial;
+  const uint32_t* inj_step;
+  const uint32_t* inj_reset;
+  const uint32_t* inj_act;
+  unsigned long long* stats;
+  uint32_t* err;
+  uint64_t tick;
+  int64_t N;
+  int32_t actions_dtype, rewards_dtype;
+};
+
+struct ResetParams {
+  DevConfig c;
+  StateArrays st;
+  const uint8_t* mask;
+  const uint32_t* inj_reset;
+  uint64_t tick;
+  int64_t N;
+};
+
+struct EncodeParams {
+  DevConfig c;
+  DevEncode enc;
+  StateArrays st;      // k_encode_env
+  const void* rows;    // k_encode_rows
+  float* spatial;
+  float* non_spatial;
+  int64_t n_items;
+};
+
+struct ExportParams {
+  DevConfig c;
+  StateArrays st;
+  void* out;
+  int64_t N;
+};
+
+struct ImportParams {
+  DevConfig c;
+  StateArrays st;
+  const long long* flat;
+  const uint8_t* imp;
+  const int32_t* t;
+  int64_t N;
+};
+
+struct ActParams {
+  DevConfig c;
+  StateArrays st;
+  int32_t* out;
+  const uint32_t* inj_act;
+  uint64_t tick;
+  int64_t N;
+};
+
+// ------------------------------------------------------------------------------------------ kernels
+__device__ __forceinline__ uint32_t role_actions_rt(const DevConfig& c, uint32_t is_imp) {
+  if (c.variant == SUS_VARIANT_TRAINING_GROUND) return 5u + is_imp;
+  const uint32_t base = 6u + is_imp;
+  return c.variant == SUS_VARIANT_TAGGING ? base + (uint32_t)c.A - 1u : base;
+}
+
+__global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ ResetParams p) {
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= p.N) return;
+  if (p.mask && !p.mask[e]) return;
+  EnvState s;
+  WordStream ws;
+  ws.init(p.c, p.inj_reset ? p.inj_reset + e * (p.c.nI + p.c.A + p.c.J) : nullptr, (uint32_t)e, p.tick, P_RESET);
+  reset_env(p.c, tb, s, ws);
+  store_state(p.st, e, s, true);
+}
+
+template <int VARIANT, bool ENCODE>
+__global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepParams p) {
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const DevConfig& c = p.c;
+  const int A = c.A;
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t e0 = e - lane;
+  const bool have = e < p.N;
+  bool stepped = false, finished = false;
+  EnvState s = {};
+  StepResult r = {};
+  if (have) {
+    load_state(p.st, e, s);
+    // ---- actions: role-list indices, one byte per agent
+    uint64_t acts = 0;
+    bool ok = true;
+    if (p.actions == nullptr) {  // fused random policy == env.step(env.sample_actions()), base.py:326-330
+      WordStream wa;
+      wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, p.tick, P_ACT_FUSED);
+      for (int i = 0; i < A; ++i)
+        acts |= (uint64_t)bounded(wa.word(i), n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) << (8 * i);
+    } else {
+      for (int i = 0; i < A; ++i) {
+        long long a;
+        if (p.actions_dtype == SUS_I32) a = static_cast<const int32_t*>(p.actions)[e * A + i];
+        else if (p.actions_dtype == SUS_I64) a = static_cast<const long long*>(p.actions)[e * A + i];
+        else a = static_cast<const uint8_t*>(p.actions)[e * A + i];
+        if (a < 0 || a >= (long long)n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) { ok = false; a = 0; }
+        acts |= (uint64_t)a << (8 * i);
+      }
+    }
+    if (p.actions_out)
+      for (int i = 0; i < A; ++i) p.actions_out[e * A + i] = (int32_t)get_byte(acts, i);
+    if (ok) {
+      WordStream ws;
+      ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, p.tick, P_STEP);
+      step_env<VARIANT>(c, tb, s, acts, ws, r);
+      stepped = true;
+      finished = r.done || r.trunc;
+      if (p.rewards) {
+        if (p.rewards_dtype == SUS_F64) {
+          double* o = static_cast<double*>(p.rewards) + e * A;
+          for (int i = 0; i < A; ++i) o[i] = agent_reward<VARIANT>(c, s, r, i);
+        } else {
+          float* o = static_cast<float*>(p.rewards) + e * A;
+          for (int i = 0; i < A; ++i) o[i] = (float)agent_reward<VARIANT>(c, s, r, i);
+        }
+      }
+      if (p.done) p.done[e] = r.done;
+      if (p.trunc) p.trunc[e] = r.trunc;
+      if (p.next_flat) write_flat<float>(c, s, p.next_flat + e * c.S);
+      if (p.metrics) {
+        long long* m = p.metrics + e * SUS_N_METRICS;
+        m[SUS_M_TOTAL_TIME_STEPS] = s.nsteps; m[SUS_M_IMP_KILLED_CREW] = s.misc & 0xff;
+        m[SUS_M_COMPLETED_JOBS] = s.completed; m[SUS_M_SABOTAGED_JOBS] = s.sabotaged;
+        m[SUS_M_IMP_VOTED_OUT] = (s.misc >> 8) & 0xff; m[SUS_M_CREW_VOTED_OUT] = (s.misc >> 16) & 0xff;
+        m[SUS_M_CREW_WON] = (s.misc >> 24) & 1u; m[SUS_M_IMPOSTER_WON] = (s.misc >> 25) & 1u;
+      }
+    } else {
+      atomicAdd(p.err, 1u);
+    }
+  }
+  // ---- finished-episode statistics: warp reduction, one atomic per statistic per warp
+  if (__any_sync(kFull, finished)) {
+    const uint32_t f = finished ? 1u : 0u;
+    uint32_t v[SUS_N_STATS];
+    v[SUS_S_EPISODES] = f; v[SUS_S_CREW_WON] = f * ((s.misc >> 24) & 1u); v[SUS_S_IMPOSTER_WON] = f * ((s.misc >> 25) & 1u);
+    v[SUS_S_IMP_KILLED_CREW] = f * (s.misc & 0xff); v[SUS_S_COMPLETED_JOBS] = f * s.completed;
+    v[SUS_S_SABOTAGED_JOBS] = f * s.sabotaged; v[SUS_S_IMP_VOTED_OUT] = f * ((s.misc >> 8) & 0xff);
+    v[SUS_S_CREW_VOTED_OUT] = f * ((s.misc >> 16) & 0xff); v[SUS_S_TOTAL_TIME_STEPS] = f * s.nsteps;
+    v[SUS_S_TRUNCATED] = (finished && r.trunc) ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < SUS_N_STATS; ++k) {
+      // 32 lanes x < 2^26 each cannot overflow 32 bits for any sane episode length
+      const uint32_t sum = __reduce_add_sync(kFull, v[k]);
+      if (lane == 0 && sum) atomicAdd(p.stats + k, (unsigned long long)sum);
+    }
+  }
+  if (stepped) {
+    if (finished && c.auto_reset) {  // SURVEY.md A.7; train.py:419-445 does this on the host
+      WordStream wr;
+      wr.init(c, p.inj_reset ? p.inj_reset + e * (c.nI + A + c.J) : nullptr, (uint32_t)e, p.tick, P_AUTORESET);
+      reset_env(c, tb, s, wr);
+      store_state(p.st, e, s, true);
+    } else {
+      store_state(p.st, e, s, false);
+    }
+  }
+  if (ENCODE) {
+    const int64_t rem = p.N - e0;
+    warp_encode(c, p.enc, tb, obs_of(s), e0, rem < 32 ? (int)(rem < 0 ? 0 : rem) : 32, have, p.N, p.spatial, p.non_spatial);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_sample_actions(const __grid_constant__ ActParams p) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= p.N) return;
+  const uint32_t imp = (p.st.aux[e].x >> 8) & 0xff;
+  WordStream wa;
+  wa.init(p.c, p.inj_act ? p.inj_act + e * p.c.A : nullptr, (uint32_t)e, p.tick, P_ACT);
+  for (int i = 0; i < p.c.A; ++i)  // base.py:326-330 (R6): dead agents are sampled too
+    p.out[e * p.c.A + i] = (int32_t)bounded(wa.word(i), role_actions_rt(p.c, (imp >> i) & 1u));
+}
+
+__global__ void __launch_bounds__(kThreads) k_encode_env(const __grid_constant__ EncodeParams p) {
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x, e0 = e - lane;
+  const bool have = e < p.n_items;
+  EnvState s = {};
+  if (have) load_state(p.st, e, s);
+  const int64_t rem = p.n_items - e0;
+  warp_encode(p.c, p.enc, tb, obs_of(s), e0, rem < 32 ? (int)(rem < 0 ? 0 : rem) : 32, have, p.n_items, p.spatial,
+              p.non_spatial);
+}
+
+// unflatten one row (gymnasium.spaces.unflatten casts to int64: truncation) into the packed observation
+template <typename T>
+__device__ __forceinline__ ObsState parse_row(const DevConfig& c, const T* __restrict__ row) {
+  ObsState o = {};
+  const int A = c.A, J = c.J;
+  int k = 0;
+  for (int i = 0; i < A; ++i) {
+    const long long x = (long long)row[k], y = (long long)row[k + 1];
+    k += 2;
+    const uint32_t code = (x >= 0 && x <= 8 && y >= 0 && y <= 8) ? (uint32_t)((x << 4) | y) : 0xffu;
+    o.pos |= (uint64_t)code << (8 * i);
+  }
+  for (int i = 0; i < A; ++i) o.alive |= ((long long)row[k++] != 0 ? 1u : 0u) << i;
+  if (J > 0 || c.variant == SUS_VARIANT_TAGGING) {
+    for (int j = 0; j < J; ++j) {
+      const long long x = (long long)row[k], y = (long long)row[k + 1];
+      k += 2;
+      const uint32_t code = (x >= 0 && x <= 8 && y >= 0 && y <= 8) ? (uint32_t)((x << 4) | y) : 0xffu;
+      o.jobpos |= (uint64_t)code << (8 * j);
+    }
+    for (int j = 0; j < J; ++j) o.jobdone |= ((long long)row[k++] != 0 ? 1u : 0u) << j;
+  }
+  if (c.variant == SUS_VARIANT_TAGGING) {
+    for (int i = 0; i < A; ++i) o.used |= ((long long)row[k++] != 0 ? 1u : 0u) << i;
+    for (int i = 0; i < A; ++i) {
+      long long t = (long long)row[k++];
+      t = t < 0 ? 0 : (t > 15 ? 15 : t);
+      o.tagcnt |= (uint32_t)t << (4 * i);
+    }
+  }
+  return o;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_encode_rows(const __grid_constant__ EncodeParams p) {
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x, e0 = e - lane;
+  const bool have = e < p.n_items;
+  ObsState o = {};
+  if (have) o = parse_row<T>(p.c, static_cast<const T*>(p.rows) + e * p.c.S);
+  const int64_t rem = p.n_items - e0;
+  warp_encode(p.c, p.enc, tb, o, e0, rem < 32 ? (int)(rem < 0 ? 0 : rem) : 32, have, p.n_items, p.spatial, p.non_spatial);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_export_flat(const __grid_constant__ ExportParams p) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= p.N) return;
+  EnvState s;
+  load_state(p.st, e, s);
+  write_flat<T>(p.c, s, static_cast<T*>(p.out) + e * p.c.S);
+}
+
+__global__ void __launch_bounds__(kThreads) k_export_imp(const __grid_constant__ ExportParams p) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= p.N) return;
+  const uint32_t imp = (p.st.aux[e].x >> 8) & 0xff;
+  for (int i = 0; i < p.c.A; ++i) static_cast<uint8_t*>(p.out)[e * p.c.A + i] = (imp >> i) & 1u;
+}
+
+__global__ void __launch_bounds__(kThreads) k_export_metrics(const __grid_constant__ ExportParams p) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= p.N) return;
+  EnvState s;
+  load_state(p.st, e, s);
+  long long* m = static_cast<long long*>(p.out) + e * SUS_N_METRICS;
+  m[SUS_M_TOTAL_TIME_STEPS] = s.nsteps; m[SUS_M_IMP_KILLED_CREW] = s.misc & 0xff;
+  m[SUS_M_COMPLETED_JOBS] = s.completed; m[SUS_M_SABOTAGED_JOBS] = s.sabotaged;
+  m[SUS_M_IMP_VOTED_OUT] = (s.misc >> 8) & 0xff; m[SUS_M_CREW_VOTED_OUT] = (s.misc >> 16) & 0xff;
+  m[SUS_M_CREW_WON] = (s.misc >> 24) & 1u; m[SUS_M_IMPOSTER_WON] = (s.misc >> 25) & 1u;
+}
+
+__global__ void __launch_bounds__(kThreads) k_import_flat(const __grid_constant__ ImportParams p) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= p.N) return;
+  const DevConfig& c = p.c;
+  const ObsState o = parse_row<long long>(c, p.flat + e * c.S);
+  EnvState s = {};
+  s.pos = o.pos; s.jobpos = o.jobpos; s.alive = o.alive; s.jobdone = o.jobdone; s.used = o.used; s.tagcnt = o.tagcnt;
+  if (c.variant == SUS_VARIANT_TAGGING) s.timer = (uint32_t)((long long)c.tag_interval - p.flat[e * c.S + c.S - 1]);
+  for (int i = 0; i < c.A; ++i) s.imp |= (p.imp[e * c.A + i] ? 1u : 0u) << i;
+  s.nsteps = p.t ? (uint32_t)p.t[e] : 0u;
+  store_state(p.st, e, s, true);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+int flat_size(const SusConfig& c) {
+  const int A = c.n_imposters + c.n_crew, J = c.n_jobs;
+  int S = 3 * A + ((J > 0 || c.variant == SUS_VARIANT_TAGGING) ? 3 * J : 0);  // base.py:211-228
+  if (c.variant == SUS_VARIANT_TAGGING) S += 2 * A + 1;                        // tagging.py:42-60
+  return S;
+}
+
+int validate_config(const SusConfig& c) {
+  // _validate_init_args: base.py:243-249, pred_prey.py:75-76
+  if (c.variant < 0 || c.variant > 2) return fail(SUS_ERR_INVALID_ARGUMENT, "unknown variant");
+  if (c.variant == SUS_VARIANT_TRAINING_GROUND) {
+    if (c.n_crew <= 0) return fail(SUS_ERR_INVALID_ARGUMENT, "Must have at least one crew member.");
+    if (c.n_imposters != 1) return fail(SUS_ERR_INVALID_ARGUMENT, "ImposterTrainingGround has exactly one imposter");
+  } else {
+    if (c.n_imposters <= 0) return fail(SUS_ERR_INVALID_ARGUMENT, "Must have at least one imposter.");
+    if (c.n_crew <= 0) return fail(SUS_ERR_INVALID_ARGUMENT, "Must have at least one crew member.");
+    if (c.n_imposters >= c.n_crew) return fail(SUS_ERR_INVALID_ARGUMENT, "Must be more crew members than imposters.");
+  }
+  if (c.n_jobs < 0) return fail(SUS_ERR_INVALID_ARGUMENT, "Must non-negative jobs.");
+  if (c.n_imposters + c.n_crew > SUS_MAX_AGENTS) return fail(SUS_ERR_UNSUPPORTED, "more than 8 agents is not supported");
+  if (c.n_jobs > SUS_MAX_JOBS) return fail(SUS_ERR_UNSUPPORTED, "more than 8 jobs is not supported");
+  if (c.variant == SUS_VARIANT_TAGGING && c.n_jobs == 0)
+    return fail(SUS_ERR_UNSUPPORTED, "the tagging env with n_jobs == 0 has no consistent state layout in the reference");
+  if (c.max_time_steps < 1) return fail(SUS_ERR_INVALID_ARGUMENT, "max_time_steps must be >= 1");
+  if (c.variant == SUS_VARIANT_TAGGING && c.tag_reset_interval < 1)
+    return fail(SUS_ERR_INVALID_ARGUMENT, "tag_reset_interval must be >= 1");
+  if (c.num_envs < 0 || (uint64_t)c.env_id_base + (uint64_t)c.num_envs > 0x100000000ull)
+    return fail(SUS_ERR_INVALID_ARGUMENT, "env_id_base + num_envs must fit in 32 bits");
+  return SUS_OK;
+}
+
+void make_dev_config(const SusConfig& c, DevConfig& d) {
+  std::memset(&d, 0, sizeof(d));
+  d.variant = c.variant; d.nI = c.n_imposters; d.A = c.n_imposters + c.n_crew; d.J = c.n_jobs;
+  d.S = flat_size(c);
+  d.order_random = c.is_action_order_random; d.shuffle_imp = c.shuffle_imposter_index; d.auto_reset = c.auto_reset;
+  d.max_time_steps = (uint32_t)c.max_time_steps; d.tag_interval = (uint32_t)c.tag_reset_interval;
+  d.seed_lo = (uint32_t)c.seed; d.seed_hi = (uint32_t)(c.seed >> 32); d.env_id_base = c.env_id_base;
+  d.r_kill = c.kill_reward; d.r_fix = c.complete_job_reward; d.r_sab = c.sabotage_reward; d.r_tsr = c.time_step_reward;
+  d.r_end = c.game_end_reward; d.r_dead = c.dead_penalty; d.r_vote = c.vote_reward;
+  // geometry: base.py:171-199
+  static const int walls[13][2] = {{0, 4}, {2, 4}, {3, 4}, {4, 4}, {5, 4}, {6, 4}, {8, 4},
+                                   {4, 0}, {4, 2}, {4, 3}, {4, 5}, {4, 6}, {4, 8}};
+  bool grid[9][9];
+  for (auto& row : grid) for (bool& g : row) g = true;
+  if (c.include_walls) for (auto& w : walls) grid[w[0]][w[1]] = false;
+  int V = 0;
+  for (int x = 0; x < 9; ++x)
+    for (int y = 0; y < 9; ++y)
+      if (grid[x][y]) {
+        const uint32_t code = (uint32_t)(x << 4 | y);
+        d.valid_bits[code >> 5] |= 1u << (code & 31u);
+        d.cell_code[V++] = (uint8_t)code;
+      }
+  d.V = V;
+}
+
+int component_size(const SusConfig& c, int comp) {
+  const int A = c.n_imposters + c.n_crew;
+  switch (comp) {
+    case SUS_FC_ONEHOT_POS: return A * 18;
+    case SUS_FC_COORDS: return 2 * A;
+    case SUS_FC_ALIVE_CREW: return A - 1;
+    case SUS_FC_CLOSEST_CREW: return c.n_imposters == 1 ? c.n_crew : -1;  // indexes l1_crew[agent_idx - 1]
+    case SUS_FC_L1_CREW: return c.n_imposters == 1 ? c.n_crew : -1;
+    case SUS_FC_DIST_TO_IMPOSTER: return 2 * (A - 1);
+    case SUS_FC_WALLS: return 9;
+    case SUS_FC_ROOMS: return 8;
+    case SUS_FC_SCENT: return 4;
+    case SUS_FC_STATE_ALIVE: return A;
+    case SUS_FC_STATE_JOB_STATUS: return c.n_jobs;
+    case SUS_FC_STATE_USED_TAGS: return c.variant == SUS_VARIANT_TAGGING ? A : -1;
+    case SUS_FC_STATE_TAG_COUNTS: return c.variant == SUS_VARIANT_TAGGING ? A : -1;
+  }
+  return -1;
+}
+
+int make_dev_encode(const SusConfig& c, const SusEncodeSpec* spec, DevEncode& d, SusEncodeShape* shape) {
+  std::memset(&d, 0, sizeof(d));
+  const int A = c.n_imposters + c.n_crew, J = c.n_jobs;
+  SusEncodeShape sh = {0, 0, 0, 0};
+  if (!spec || spec->kind == SUS_ENCODE_NONE) {
+    d.kind = SUS_ENCODE_NONE;
+  } else if (spec->kind == SUS_ENCODE_GLOBAL || spec->kind == SUS_ENCODE_PERSPECTIVE) {
+    if (J == 0)  // the reference raises IndexError: the state tuple has no job fields
+      return fail(SUS_ERR_INVALID_ARGUMENT, "Global/Perspective featurizers need n_jobs > 0");
+    const int tags = c.variant == SUS_VARIANT_TAGGING ? A : 0;
+    d.kind = spec->kind;
+    sh.spatial_floats = (A + 2) * 81;
+    sh.non_spatial_views = A;
+    if (spec->kind == SUS_ENCODE_GLOBAL) { sh.spatial_views = 1; sh.non_spatial_floats = A + tags + J + A; }
+    else { sh.spatial_views = A; sh.non_spatial_floats = A + tags + J; }
+  } else if (spec->kind == SUS_ENCODE_FLAT) {
+    if (spec->n_components < 1 || spec->n_components > SUS_MAX_FLAT_COMPONENTS)
+      return fail(SUS_ERR_INVALID_ARGUMENT, "flat encode needs 1..16 components");
+    d.kind = SUS_ENCODE_FLAT;
+    d.n_components = spec->n_components;
+    int F = 0;
+    for (int q = 0; q < spec->n_components; ++q) {
+      const int n = component_size(c, spec->components[q]);
+      if (n < 0) return fail(SUS_ERR_INVALID_ARGUMENT, "flat component " + std::to_string(spec->components[q]) + " is not defined for this env");
+      d.components[q] = spec->components[q];
+      F += n;
+    }
+    sh.non_spatial_floats = F;
+    sh.non_spatial_views = 1;
+  } else {
+    return fail(SUS_ERR_INVALID_ARGUMENT, "unknown encode kind");
+  }
+  d.sp_floats = sh.spatial_floats;
+  d.ns_floats = sh.non_spatial_floats;
+  if (shape) *shape = sh;
+  return SUS_OK;
+}
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+int after_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SUS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return SUS_OK;
+}
+
+}  // namespace
+
+struct SusEnv {
+  SusConfig cfg;
+  DevConfig dc;
+  int device;
+  int64_t N;
+  StateArrays st;
+  unsigned long long* stats;
+  uint32_t* err;
+  uint64_t step_tick, reset_epoch, act_epoch;
+  const uint32_t *inj_step, *inj_reset, *inj_act;
+};
+
+extern "C" {
+
+int sus_abi_version(void) { return SUS_ABI_VERSION; }
+const char* sus_last_error(void) { return g_last_error.c_str(); }
+int64_t sus_launch_count(void) { return g_launches.load(); }
+
+int sus_flat_state_size(const SusConfig* cfg) {
+  if (!cfg) return fail(SUS_ERR_INVALID_ARGUMENT, "cfg is NULL");
+  if (int rc = validate_config(*cfg)) return rc;
+  return flat_size(*cfg);
+}
+
+int sus_n_role_actions(const SusConfig* cfg, int is_imposter) {
+  if (!cfg) return fail(SUS_ERR_INVALID_ARGUMENT, "cfg is NULL");
+  if (int rc = validate_config(*cfg)) return rc;
+  const int A = cfg->n_imposters + cfg->n_crew;
+  if (cfg->variant == SUS_VARIANT_TRAINING_GROUND) return is_imposter ? 6 : 5;
+  const int base = is_imposter ? 7 : 6;
+  return cfg->variant == SUS_VARIANT_TAGGING ? base + A - 1 : base;
+}
+
+int sus_encode_shape(const SusConfig* cfg, const SusEncodeSpec* spec, SusEncodeShape* out) {
+  if (!cfg || !spec || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (int rc = validate_config(*cfg)) return rc;
+  DevEncode d;
+  return make_dev_encode(*cfg, spec, d, out);
+}
+
+int sus_env_create(const SusConfig* cfg, int device, sus_env_t* out) {
+  if (!cfg || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (int rc = validate_config(*cfg)) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SUS_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
+  SusEnv* e = new SusEnv();
+  e->cfg = *cfg;
+  make_dev_config(*cfg, e->dc);
+  e->device = device;
+  e->N = cfg->num_envs;
+  const size_t n = (size_t)(e->N > 0 ? e->N : 1);
+  cudaError_t err = cudaSuccess;
+  if (err == cudaSuccess) err = cudaMalloc(&e->st.pos, n * sizeof(uint64_t));
+  if (err == cudaSuccess) err = cudaMalloc(&e->st.jobpos, n * sizeof(uint64_t));
+  if (err == cudaSuccess) err = cudaMalloc(&e->st.aux, n * sizeof(uint4));
+  if (err == cudaSuccess) err = cudaMalloc(&e->st.met, n * sizeof(uint4));
+  if (err == cudaSuccess) err = cudaMalloc(&e->stats, SUS_N_STATS * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMalloc(&e->err, sizeof(uint32_t));
+  if (err == cudaSuccess) err = cudaMemset(e->st.pos, 0, n * sizeof(uint64_t));
+  if (err == cudaSuccess) err = cudaMemset(e->st.jobpos, 0, n * sizeof(uint64_t));
+  if (err == cudaSuccess) err = cudaMemset(e->st.aux, 0, n * sizeof(uint4));
+  if (err == cudaSuccess) err = cudaMemset(e->st.met, 0, n * sizeof(uint4));
+  if (err == cudaSuccess) err = cudaMemset(e->stats, 0, SUS_N_STATS * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(e->err, 0, sizeof(uint32_t));
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    const std::string msg = std::string("allocating env state: ") + cudaGetErrorString(err);
+    sus_env_destroy(e);
+    return fail(SUS_ERR_CUDA, msg);
+  }
+  *out = e;
+  return SUS_OK;
+}
+
+int sus_env_destroy(sus_env_t e) {
+  if (!e) return SUS_OK;
+  DeviceGuard g(e->device);
+  cudaDeviceSynchronize();
+  cudaFree(e->st.pos); cudaFree(e->st.jobpos); cudaFree(e->st.aux); cudaFree(e->st.met);
+  cudaFree(e->stats); cudaFree(e->err);
+  delete e;
+  return SUS_OK;
+}
+
+int sus_env_reset(sus_env_t e, const uint8_t* mask, void* stream) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  DeviceGuard g(e->device);
+  ResetParams p;
+  p.c = e->dc; p.st = e->st; p.mask = mask; p.inj_reset = e->inj_reset; p.tick = e->reset_epoch++; p.N = e->N;
+  e->inj_reset = nullptr;
+  if (e->N == 0) return SUS_OK;
+  k_reset<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
+  return after_launch("k_reset");
+}
+
+int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
+  if (!e || !io) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (io->actions && io->actions_dtype != SUS_U8 && io->actions_dtype != SUS_I32 && io->actions_dtype != SUS_I64)
+    return fail(SUS_ERR_INVALID_ARGUMENT, "actions_dtype must be SUS_U8, SUS_I32 or SUS_I64");
+  if (io->rewards && io->rewards_dtype != SUS_F32 && io->rewards_dtype != SUS_F64)
+    return fail(SUS_ERR_INVALID_ARGUMENT, "rewards_dtype must be SUS_F32 or SUS_F64");
+  DeviceGuard g(e->device);
+  StepParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.c = e->dc;
+  if (int rc = make_dev_encode(e->cfg, io->encode, p.enc, nullptr)) return rc;
+  const bool enc = p.enc.kind != SUS_ENCODE_NONE;
+  if (enc && (!io->non_spatial || (p.enc.sp_floats > 0 && !io->spatial)))
+    return fail(SUS_ERR_INVALID_ARGUMENT, "fused encode requested without output tensors");
+  p.st = e->st;
+  p.actions = io->actions; p.actions_dtype = io->actions_dtype; p.rewards = io->rewards; p.rewards_dtype = io->rewards_dtype;
+  p.done = io->done; p.trunc = io->truncated; p.actions_out = io->actions_out; p.next_flat = io->next_flat;
+  p.metrics = reinterpret_cast<long long*>(io->metrics); p.spatial = io->spatial; p.non_spatial = io->non_spatial;
+  p.inj_step = e->inj_step; p.inj_reset = e->inj_reset; p.inj_act = e->inj_act;
+  p.stats = e->stats; p.err = e->err; p.tick = e->step_tick++; p.N = e->N;
+  e->inj_step = e->inj_reset = e->inj_act = nullptr;
+  if (e->N == 0) return SUS_OK;
+  const unsigned gr = grid_for(e->N);
+  cudaStream_t st = (cudaStream_t)stream;
+#define SUS_LAUNCH_STEP(V)                                      \
+  if (enc) k_step<V, true><<<gr, kThreads, 0, st>>>(p);         \
+  else k_step<V, false><<<gr, kThreads, 0, st>>>(p)
+  switch (e->cfg.variant) {
+    case SUS_VARIANT_BASE: SUS_LAUNCH_STEP(SUS_VARIANT_BASE); break;
+    case SUS_VARIANT_TAGGING: SUS_LAUNCH_STEP(SUS_VARIANT_TAGGING); break;
+    default: SUS_LAUNCH_STEP(SUS_VARIANT_TRAINING_GROUND); break;
+  }
+#undef SUS_LAUNCH_STEP
+  return after_launch("k_step");
+}
+
+int sus_env_check_actions(sus_env_t e, void* stream) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  DeviceGuard g(e->device);
+  uint32_t n = 0;
+  SUS_CUDA(cudaMemcpyAsync(&n, e->err, sizeof(n), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SUS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (n) {
+    SUS_CUDA(cudaMemsetAsync(e->err, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    return fail(SUS_ERR_INVALID_ACTION, std::to_string(n) + " env step(s) received an action index outside the agent's role list");
+  }
+  return SUS_OK;
+}
+
+int sus_env_sample_actions(sus_env_t e, int32_t* out, void* stream) {
+  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard g(e->device);
+  ActParams p;
+  p.c = e->dc; p.st = e->st; p.out = out; p.inj_act = e->inj_act; p.tick = e->act_epoch++; p.N = e->N;
+  e->inj_act = nullptr;
+  if (e->N == 0) return SUS_OK;
+  k_sample_actions<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
+  return after_launch("k_sample_actions");
+}
+
+int sus_env_export_flat(sus_env_t e, int32_t dtype, void* out, void* stream) {
+  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard g(e->device);
+  ExportParams p;
+  p.c = e->dc; p.st = e->st; p.out = out; p.N = e->N;
+  if (e->N == 0) return SUS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SUS_F32) k_export_flat<float><<<grid_for(e->N), kThreads, 0, st>>>(p);
+  else if (dtype == SUS_F64) k_export_flat<double><<<grid_for(e->N), kThreads, 0, st>>>(p);
+  else if (dtype == SUS_I64) k_export_flat<long long><<<grid_for(e->N), kThreads, 0, st>>>(p);
+  else return fail(SUS_ERR_INVALID_ARGUMENT, "export dtype must be SUS_F32, SUS_F64 or SUS_I64");
+  return after_launch("k_export_flat");
+}
+
+int sus_env_import_flat(sus_env_t e, const int64_t* flat, const uint8_t* imposter_mask, const int32_t* t, void* stream) {
+  if (!e || !flat || !imposter_mask) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard g(e->device);
+  ImportParams p;
+  p.c = e->dc; p.st = e->st; p.flat = reinterpret_cast<const long long*>(flat); p.imp = imposter_mask; p.t = t; p.N = e->N;
+  if (e->N == 0) return SUS_OK;
+  k_import_flat<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
+  return after_launch("k_import_flat");
+}
+
+int sus_env_export_imposter_mask(sus_env_t e, uint8_t* out, void* stream) {
+  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard g(e->device);
+  ExportParams p;
+  p.c = e->dc; p.st = e->st; p.out = out; p.N = e->N;
+  if (e->N == 0) return SUS_OK;
+  k_export_imp<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
+  return after_launch("k_export_imp");
+}
+
+int sus_env_export_metrics(sus_env_t e, int64_t* out, void* stream) {
+  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard g(e->device);
+  ExportParams p;
+  p.c = e->dc; p.st = e->st; p.out = out; p.N = e->N;
+  if (e->N == 0) return SUS_OK;
+  k_export_metrics<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
+  return after_launch("k_export_metrics");
+}
+
+int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float* non_spatial, void* stream) {
+  if (!e || !spec) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard g(e->device);
+  EncodeParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.c = e->dc;
+  if (int rc = make_dev_encode(e->cfg, spec, p.enc, nullptr)) return rc;
+  if (p.enc.kind == SUS_ENCODE_NONE) return fail(SUS_ERR_INVALID_ARGUMENT, "encode kind is NONE");
+  if (!non_spatial || (p.enc.sp_floats > 0 && !spatial)) return fail(SUS_ERR_INVALID_ARGUMENT, "missing output tensor");
+  p.st = e->st; p.spatial = spatial; p.non_spatial = non_spatial; p.n_items = e->N;
+  if (e->N == 0) return SUS_OK;
+  k_encode_env<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
+  return after_launch("k_encode_env");
+}
+
+int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const void* states, int32_t dtype,
+                         int64_t n_items, float* spatial, float* non_spatial, int device, void* stream) {
+  if (!cfg || !spec || !states) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (int rc = validate_config(*cfg)) return rc;
+  if (n_items < 0) return fail(SUS_ERR_INVALID_ARGUMENT, "n_items < 0");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SUS_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
+  EncodeParams p;
+  std::memset(&p, 0, sizeof(p));
+  make_dev_config(*cfg, p.c);
+  if (int rc = make_dev_encode(*cfg, spec, p.enc, nullptr)) return rc;
+  if (p.enc.kind == SUS_ENCODE_NONE) return fail(SUS_ERR_INVALID_ARGUMENT, "encode kind is NONE");
+  if (!non_spatial || (p.enc.sp_floats > 0 && !spatial)) return fail(SUS_ERR_INVALID_ARGUMENT, "missing output tensor");
+  p.rows = states; p.spatial = spatial; p.non_spatial = non_spatial; p.n_items = n_items;
+  if (n_items == 0) return SUS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SUS_F32) k_encode_rows<float><<<grid_for(n_items), kThreads, 0, st>>>(p);
+  else if (dtype == SUS_F64) k_encode_rows<double><<<grid_for(n_items), kThreads, 0, st>>>(p);
+  else if (dtype == SUS_I64) k_encode_rows<long long><<<grid_for(n_items), kThreads, 0, st>>>(p);
+  else return fail(SUS_ERR_INVALID_ARGUMENT, "states dtype must be SUS_F32, SUS_F64 or SUS_I64");
+  return after_launch("k_encode_rows");
+}
+
+int sus_env_stats(sus_env_t e, int64_t* out, void* stream) {
+  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard g(e->device);
+  SUS_CUDA(cudaMemcpyAsync(out, e->stats, SUS_N_STATS * sizeof(int64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SUS_OK;
+}
+
+int sus_env_clear_stats(sus_env_t e, void* stream) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  DeviceGuard g(e->device);
+  SUS_CUDA(cudaMemsetAsync(e->stats, 0, SUS_N_STATS * sizeof(int64_t), (cudaStream_t)stream));
+  return SUS_OK;
+}
+
+int sus_env_get_ticks(sus_env_t e, uint64_t* step_tick, uint64_t* reset_epoch, uint64_t* act_epoch) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (step_tick) *step_tick = e->step_tick;
+  if (reset_epoch) *reset_epoch = e->reset_epoch;
+  if (act_epoch) *act_epoch = e->act_epoch;
+  return SUS_OK;
+}
+
+int sus_env_set_ticks(sus_env_t e, uint64_t step_tick, uint64_t reset_epoch, uint64_t act_epoch) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  e->step_tick = step_tick; e->reset_epoch = reset_epoch; e->act_epoch = act_epoch;
+  return SUS_OK;
+}
+
+int sus_env_state_arrays(sus_env_t e, void** ptrs, int32_t* bytes_per_env) {
+  if (!e || !ptrs || !bytes_per_env) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  ptrs[0] = e->st.pos; ptrs[1] = e->st.jobpos; ptrs[2] = e->st.aux; ptrs[3] = e->st.met;
+  bytes_per_env[0] = 8; bytes_per_env[1] = 8; bytes_per_env[2] = 16; bytes_per_env[3] = 16;
+  return SUS_OK;
+}
+
+int sus_env_debug_inject_words(sus_env_t e, const uint32_t* step_words, const uint32_t* reset_words,
+                               const uint32_t* act_words) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (step_words) e->inj_step = step_words;
+  if (reset_words) e->inj_reset = reset_words;
+  if (act_words) e->inj_act = act_words;
+  return SUS_OK;
+}
+
+}  // extern "C"

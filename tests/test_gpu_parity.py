@@ -1,0 +1,283 @@
+"""GPU: the CUDA path (through the C ABI + the host mirror) against the golden fixtures minted from the reference
+and against the oracle on seeded inputs.  Integer state, dones, truncations, metrics: bit-exact.  Rewards: exact
+(float64 path compares bit patterns incl. the sign of zero; the float32 replay-layout path compares values).
+Features: bit-exact float32 (tolerance stated by the north star is 1e-6; exact construction meets it with 0)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.cases import FLAT_COMPONENT_SETS, GLOBAL_CASES
+from tests.util import CASES, case_of, flat_featurizer, golden_files, load, make_cuda_env, reward_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def replay_cuda(g, cfg):
+    T, N, A = g["actions"].shape
+    injected = bool(g["injected"])
+    env = make_cuda_env(cfg, N, seed=int(g["seed"]), env_id_base=int(g["env_id_base"]))
+    env._rewards = torch.zeros((N, A), dtype=torch.float64, device=env.device)  # numpy-identical reward path
+    env._metrics_buf = torch.zeros((N, 8), dtype=torch.int64, device=env.device)
+    if injected:
+        env.debug_inject_words(reset_words=g["reset_words0"])
+    flat, _ = env.reset()
+    assert np.array_equal(cpu(flat).astype(np.int64), g["reset_flat"])
+    assert np.array_equal(cpu(env.imposter_mask_batch).astype(np.uint8), g["reset_imp"])
+    for t in range(T):
+        if injected:
+            env.debug_inject_words(act_words=g["act_words"][t])
+        a = cpu(env.sample_actions())
+        if t % 7 != 3:
+            assert np.array_equal(a, g["actions"][t]), f"sample_actions differs at step {t}"
+        if injected:
+            env.debug_inject_words(step_words=g["step_words"][t], reset_words=g["reset_words"][t])
+        nf, r, d, tr, _ = env.step(torch.as_tensor(g["actions"][t].astype(np.int32)), check=True)
+        assert np.array_equal(cpu(nf).astype(np.int64), g["next_flat"][t]), f"state differs at step {t}"
+        assert np.array_equal(reward_bits(cpu(r)), reward_bits(g["rewards"][t])), f"rewards differ at step {t}"
+        assert np.array_equal(cpu(d), g["done"][t] != 0) and np.array_equal(cpu(tr), g["trunc"][t] != 0)
+        assert np.array_equal(cpu(env._metrics_buf), g["metrics"][t]), f"metrics differ at step {t}"
+        assert np.array_equal(cpu(env.flat_states(torch.int64)), g["cur_flat"][t]), f"post-reset state differs at {t}"
+        assert np.array_equal(cpu(env.imposter_mask_batch).astype(np.uint8), g["imp"][t])
+    fin = (g["done"] | g["trunc"]) != 0
+    st = cpu(env.episode_stats())
+    assert st[0] == fin.sum() and st[9] == (g["trunc"] != 0).sum() and st[8] == g["metrics"][..., 0][fin].sum()
+
+
+@pytest.mark.parametrize("path", golden_files("philox"), ids=case_of)
+def test_cuda_matches_reference_philox_draws(cuda_lib, path):
+    replay_cuda(load(path), CASES[case_of(path)])
+
+
+@pytest.mark.parametrize("path", golden_files("words"), ids=case_of)
+def test_cuda_matches_reference_injected_words(cuda_lib, path):
+    replay_cuda(load(path), CASES[case_of(path)])
+
+
+@pytest.mark.parametrize("path", golden_files("features"), ids=case_of)
+def test_cuda_features_match_reference(cuda_lib, path):
+    import sus_net_b200 as S
+
+    g = load(path)
+    name = case_of(path)
+    env = make_cuda_env(CASES[name], 4, seed=1)
+    flat = g["flat"].astype(np.int64)
+    n = flat.shape[0]
+    for dtype in (torch.float32, torch.float64, torch.int64):
+        seq = torch.as_tensor(flat).to(dtype).reshape(n // 4, 4, -1)  # (B, T, S) with T = 4
+        if "global_spatial" in g:
+            f = S.GlobalFeaturizer(env)
+            f.fit(seq)
+            views = f.generate_featurized_states()
+            assert len(views) == env.n_agents
+            for k, (sp, ns) in enumerate(views):
+                assert tuple(sp.shape) == (n // 4, 4, env.n_agents + 2, 9, 9) and sp.requires_grad
+                assert np.array_equal(cpu(sp).reshape(n, -1, 9, 9), g["global_spatial"].astype(np.float32))
+                assert np.array_equal(cpu(ns).reshape(n, -1), g["global_non_spatial"][k])
+            f = S.PerspectiveFeaturizer(env)
+            f.fit(seq)
+            for k, (sp, ns) in enumerate(f.generate_featurized_states()):
+                assert np.array_equal(cpu(sp).reshape(n, -1, 9, 9), g["perspective_spatial"][k].astype(np.float32))
+                assert np.array_equal(cpu(ns).reshape(n, -1), g["perspective_non_spatial"][k])
+        i = 0
+        while f"flat{i}" in g:
+            f = flat_featurizer(env, [str(c) for c in g[f"flat{i}_components"]])
+            f.fit(seq)
+            views = f.generate_featurized_states()
+            for sp, ns in views:
+                assert tuple(sp.shape) == (n // 4, 4, 1) and not cpu(sp).any()
+                assert np.array_equal(cpu(ns).reshape(n, -1).view(np.int32), g[f"flat{i}"].view(np.int32))
+            i += 1
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_matches_oracle_at_scale(cuda_lib, name):
+    """Seeded Philox draws, fused random policy, ragged N (not a multiple of the warp or CTA size)."""
+    cfg = CASES[name]
+    N, T, seed, base = 4099, 260, 777, 123456
+    env = make_cuda_env(cfg, N, seed=seed, env_id_base=base)
+    orc = oracle.OracleEnv(cfg, N, seed=seed, env_id_base=base)
+    flat, _ = env.reset()
+    assert np.array_equal(cpu(flat).astype(np.int64), orc.reset())
+    acts = torch.zeros((N, env.n_agents), dtype=torch.int32, device=env.device)
+    env._metrics_buf = torch.zeros((N, 8), dtype=torch.int64, device=env.device)
+    for t in range(T):
+        if t % 3 == 0:  # fused random policy
+            io_actions = None
+        else:
+            io_actions = env.sample_actions().clone()
+            assert np.array_equal(cpu(io_actions), orc.sample_actions())
+        nf, r, d, tr, _ = env.step(io_actions)
+        o = orc.step(None if io_actions is None else cpu(io_actions))
+        assert np.array_equal(cpu(nf).astype(np.int64), o["next_flat"]), f"{name}: state differs at step {t}"
+        assert np.array_equal(cpu(r), o["rewards"].astype(np.float32)), f"{name}: rewards differ at step {t}"
+        assert np.array_equal(cpu(d), o["done"] != 0) and np.array_equal(cpu(tr), o["trunc"] != 0)
+        assert np.array_equal(cpu(env._metrics_buf), o["metrics"])
+    assert np.array_equal(cpu(env.flat_states(torch.int64)), orc.flat_states())
+    assert np.array_equal(cpu(env.metrics_batch()), orc.metrics())
+    assert np.array_equal(cpu(env.episode_stats()), orc.stats())
+    env.check_actions()
+    del acts
+
+
+@pytest.mark.parametrize("name", GLOBAL_CASES + list(FLAT_COMPONENT_SETS))
+def test_fused_step_encode_matches_oracle(cuda_lib, name):
+    """The fused K1+K2 launch must write the features of the state the next action is taken from (post auto-reset)."""
+    import sus_net_b200 as S
+
+    cfg = CASES[name]
+    N, T = 1000, 120
+    env = make_cuda_env(cfg, N, seed=5, env_id_base=7)
+    orc = oracle.OracleEnv(cfg, N, seed=5, env_id_base=7)
+    env.reset(); orc.reset()
+    feats = []
+    if name in GLOBAL_CASES:
+        feats += [("global", S.GlobalFeaturizer(env)), ("perspective", S.PerspectiveFeaturizer(env))]
+    for comps in FLAT_COMPONENT_SETS.get(name, []):
+        feats.append((comps, flat_featurizer(env, comps)))
+    for t in range(T):
+        kind, f = feats[t % len(feats)]
+        env.step(None, featurizer=f)
+        orc.step(None)
+        cur = orc.flat_states()
+        views = f.generate_featurized_states()
+        if kind == "global":
+            sp, ns = oracle.encode_global(cfg, cur)
+            for k, (vsp, vns) in enumerate(views):
+                assert np.array_equal(cpu(vsp)[:, 0], sp) and np.array_equal(cpu(vns)[:, 0], ns[k])
+        elif kind == "perspective":
+            sp, ns = oracle.encode_perspective(cfg, cur)
+            for k, (vsp, vns) in enumerate(views):
+                assert np.array_equal(cpu(vsp)[:, 0], sp[k]) and np.array_equal(cpu(vns)[:, 0], ns[k])
+        else:
+            want = oracle.encode_flat(cfg, kind, cur)
+            assert np.array_equal(cpu(views[0][1])[:, 0].view(np.int32), want.view(np.int32))
+        # the standalone K2 launch on the live state must agree with the fused one
+        views2 = f.encode_env()
+        assert all(torch.equal(a[1], b[1]) and torch.equal(a[0], b[0]) for a, b in zip(views, views2))
+    assert np.array_equal(cpu(env.flat_states(torch.int64)), orc.flat_states())
+
+
+def test_reference_mode_api(cuda_lib):
+    """num_envs == 1: reset/step return what the reference returns (types, shapes, dtypes, error behaviour)."""
+    import sus_net_b200 as S
+
+    env = S.FourRoomEnv(n_imposters=1, n_crew=4, n_jobs=5, random_state=3)
+    assert env.flattened_state_size == 30 and env.n_agents == 5 and env.action_space.n == 8
+    assert env.n_imposter_actions == 7 and env.n_crew_actions == 6
+    assert env.grid.shape == (9, 9) and len(env.valid_positions) == 68 and env.valid_positions[4].tolist() == [0, 5]
+    state, info = env.reset()
+    pos, alive, jpos, jdone = state
+    assert pos.shape == (5, 2) and pos.dtype == np.int64 and alive.dtype == bool and alive.all()
+    assert jpos.shape == (5, 2) and jdone.dtype == bool and not jdone.any()
+    assert set(k.value if hasattr(k, "value") else k for k in info) >= {"total_time_steps", "crew_won", "imposter_won"}
+    assert env.imposter_mask.sum() == 1 and env.imposter_idxs.tolist() == np.where(env.imposter_mask)[0].tolist()
+    flat = env.flatten_state(state)
+    assert flat.shape == (30,) and flat.dtype == np.int64
+    un = env.unflatten_state(flat)
+    assert all(np.array_equal(a, b) for a, b in zip(un, state))
+    a = env.sample_actions()
+    assert a.shape == (5,) and all(a[i] < (7 if env.imposter_mask[i] else 6) for i in range(5))
+    nstate, r, done, trunc, info = env.step(a)
+    assert r.dtype == np.float64 and r.shape == (5,) and isinstance(done, bool) and isinstance(trunc, bool)
+    assert info[S.SusMetrics.TOTAL_TIME_STEPS] == 1
+    with pytest.raises(AssertionError):
+        env.step([0, 0, 0])  # wrong length (base.py:357-359)
+    with pytest.raises(AssertionError):
+        env.step([8, 0, 0, 0, 0])  # >= action_space.n (base.py:360-362)
+    crew = int(np.where(~env.imposter_mask)[0][0])
+    bad = [0] * 5
+    bad[crew] = 6  # crew list has 6 entries: IndexError in the reference (base.py:381)
+    with pytest.raises(IndexError):
+        env.step(bad)
+    with pytest.raises(AssertionError):
+        S.FourRoomEnv(n_imposters=2, n_crew=2, n_jobs=1)  # base.py:247-249
+    with pytest.raises(AssertionError):
+        S.ImposterTrainingGround(n_crew=0, n_jobs=0, time_step_reward=0, kill_reward=0, sabotage_reward=0,
+                                 end_of_game_reward=0)
+    # tagging env: 7-field state tuple, {} reset info (tagging.py:94-101)
+    tenv = S.FourRoomEnvWithTagging(1, 2, 5)
+    st, info = tenv.reset()
+    assert len(st) == 7 and st[6] == 50 and info == {} and tenv.flattened_state_size == 31
+    assert tenv.action_space.n == 11 and tenv.n_imposter_actions == 9 and tenv.n_crew_actions == 8
+    st, r, d, tr, info = tenv.step(tenv.sample_actions())
+    assert st[6] == 49 and len(info) == 13
+
+
+def test_reference_mode_matches_oracle_episode(cuda_lib):
+    """Drive the single-env API like train.py does (manual reset on done/trunc) against the oracle."""
+    import sus_net_b200 as S
+
+    cfg = CASES["cfg4_base_1v4"]
+    env = S.FourRoomEnv(1, 4, 5, random_state=11)
+    orc = oracle.OracleEnv(cfg, 1, seed=11, auto_reset=False)
+    state, _ = env.reset()
+    assert np.array_equal(env.flatten_state(state), orc.reset()[0])
+    for t in range(300):
+        a = env.sample_actions()
+        assert np.array_equal(a, orc.sample_actions()[0])
+        state, r, d, tr, info = env.step(a)
+        o = orc.step(a[None])
+        assert np.array_equal(env.flatten_state(state), o["next_flat"][0])
+        assert np.array_equal(reward_bits(r), reward_bits(o["rewards"][0])) and d == bool(o["done"][0])
+        assert [info[k] for k in S.METRIC_ORDER] == o["metrics"][0].tolist()
+        if d or tr:
+            state, _ = env.reset()
+            assert np.array_equal(env.flatten_state(state), orc.reset()[0])
+
+
+def test_state_dict_roundtrip_and_sharding_invariance(cuda_lib):
+    """Results depend on (seed, global env id, tick) only: two half-size shards reproduce one full-size env, and a
+    restored checkpoint continues identically."""
+    cfg = CASES["cfg3_tagging_1v2"]
+    full = make_cuda_env(cfg, 512, seed=9, env_id_base=0)
+    lo = make_cuda_env(cfg, 256, seed=9, env_id_base=0)
+    hi = make_cuda_env(cfg, 256, seed=9, env_id_base=256)
+    for e in (full, lo, hi):
+        e.reset()
+    for t in range(80):
+        nf, r, d, tr, _ = full.step(None)
+        a = lo.step(None)
+        b = hi.step(None)
+        assert torch.equal(nf, torch.cat([a[0], b[0]])) and torch.equal(r, torch.cat([a[1], b[1]]))
+        assert torch.equal(d, torch.cat([a[2], b[2]]))
+        if t == 40:
+            sd = full.state_dict()
+    assert torch.equal(full.episode_stats(), lo.episode_stats() + hi.episode_stats())
+    again = make_cuda_env(cfg, 512, seed=9, env_id_base=0)
+    again.load_state_dict(sd)
+    ref = make_cuda_env(cfg, 512, seed=9, env_id_base=0)
+    ref.reset()
+    for t in range(41):
+        ref.step(None)
+    for t in range(20):
+        assert torch.equal(again.step(None)[0], ref.step(None)[0])
+
+
+def test_empty_batch_and_survey_anchors(cuda_lib):
+    import sus_net_b200 as S
+
+    env = make_cuda_env(CASES["cfg4_base_1v4"], 0, seed=1)
+    env.reset()
+    nf, r, d, tr, _ = env.step(None)
+    assert nf.shape == (0, 30) and r.shape == (0, 5)
+    # SURVEY.md 8(c) anchors through the CUDA path
+    e = S.FourRoomEnv(1, 2, 0, shuffle_imposter_index=False)
+    e.reset()
+    _, r, d, _, _ = e.step([0, 0, 0])
+    assert r.tolist() == [-10.0, 10.0, 10.0] and d
+    e = S.ImposterTrainingGround(n_crew=2, n_jobs=0, time_step_reward=0, kill_reward=-3, sabotage_reward=0,
+                                 end_of_game_reward=0)
+    e.import_flat(np.array([[3, 3, 3, 3, 3, 3, 1, 1, 1]]), np.array([[1, 0, 0]]))
+    st, r, d, _, _ = e.step([5, 0, 0])
+    assert r.tolist() == [3.0, 0.0, 0.0] and st[1].sum() == 2 and not d
+    e = S.ImposterTrainingGround(n_crew=1, n_jobs=0, time_step_reward=0, kill_reward=-3, sabotage_reward=0,
+                                 end_of_game_reward=0)
+    e.reset()
+    for k in range(1000):
+        _, _, d, tr, _ = e.step([0, 0])
+        assert tr == (k == 999)

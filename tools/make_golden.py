@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""Mint the golden fixtures under tests/golden/ by running the UNMODIFIED reference (through the gymnasium
+stand-in and the draw-injection harness).  The reference holds no golden vectors of its own, so
+these files are how its behaviour travels to the GPU box.
+
+    python tools/make_golden.py            # writes tests/golden/*.npz
+
+Two trajectory fixtures per case:
+  <case>.philox.npz  draws follow the susnet Philox spec for the stored seed (pins Philox + draw derivation)
+  <case>.words.npz   draws are arbitrary injected 32-bit words, incl. 0 and 0xffffffff (pins the derivation's
+                     edge cases independently of Philox)
+and one feature fixture per case with the reference featurizers' outputs on states from the trajectory.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as H  # noqa: E402
+from oracle import rng_spec as R  # noqa: E402
+from tests.cases import CASES, FLAT_COMPONENT_SETS, GLOBAL_CASES  # noqa: E402
+from tools.check_oracle_vs_reference import reference_features  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+N_ENVS, N_STEPS, SEED, ENV_ID_BASE = 12, 160, 0xB200, 1000
+
+
+def edge_words(rng, shape):
+    w = rng.integers(0, 2**32, size=shape, dtype=np.uint64).astype(np.uint32)
+    m = rng.random(shape)
+    w[m < 0.05] = 0
+    w[m > 0.95] = 0xFFFFFFFF
+    return w
+
+
+def trajectory(name, injected):
+    cfg = CASES[name]
+    rng = np.random.default_rng(abs(hash(name)) % (2**31) if False else sum(map(ord, name)))
+    ref = H.ReferenceBatch(cfg, N_ENVS, SEED, env_id_base=ENV_ID_BASE)
+    A, J, nI = ref.A, ref.J, ref.cfg["n_imposters"]
+    n_rs, n_ss = R.n_reset_slots(nI, A, J), R.n_step_slots(A)
+    rec = dict(actions=[], next_flat=[], rewards=[], done=[], trunc=[], metrics=[], cur_flat=[], imp=[],
+               step_words=[], reset_words=[], act_words=[])
+    w0 = edge_words(rng, (N_ENVS, n_rs)) if injected else None
+    reset_flat = ref.reset(reset_words=w0)
+
+    def imp_mask():
+        return np.stack([np.asarray(e.imposter_mask, dtype=np.uint8) for e in ref.envs])
+
+    reset_imp = imp_mask()
+    for t in range(N_STEPS):
+        sw = edge_words(rng, (N_ENVS, n_ss)) if injected else None
+        rw = edge_words(rng, (N_ENVS, n_rs)) if injected else None
+        aw = edge_words(rng, (N_ENVS, A)) if injected else None
+        a = ref.sample_actions(act_words=aw)
+        if t % 7 == 3:  # also drive some steps with non-random actions: everybody uses the last role action
+            a = np.stack([[len(e.agent_action_map[i]) - 1 - (t // 7 + i) % 2 for i in range(A)] for e in ref.envs])
+        o = ref.step(a, step_words=sw, reset_words=rw)
+        rec["actions"].append(a); rec["next_flat"].append(o["next_flat"]); rec["rewards"].append(o["rewards"])
+        rec["done"].append(o["done"]); rec["trunc"].append(o["trunc"]); rec["metrics"].append(o["metrics"])
+        rec["cur_flat"].append(ref.flat_states()); rec["imp"].append(imp_mask())
+        if injected:
+            rec["step_words"].append(sw); rec["reset_words"].append(rw); rec["act_words"].append(aw)
+    out = dict(
+        case=name, seed=SEED, env_id_base=ENV_ID_BASE, injected=injected, reset_flat=reset_flat.astype(np.int16),
+        reset_imp=reset_imp, actions=np.array(rec["actions"], dtype=np.int8),
+        next_flat=np.array(rec["next_flat"], dtype=np.int16), rewards=np.array(rec["rewards"], dtype=np.float64),
+        done=np.array(rec["done"], dtype=np.uint8), trunc=np.array(rec["trunc"], dtype=np.uint8),
+        metrics=np.array(rec["metrics"], dtype=np.int32), cur_flat=np.array(rec["cur_flat"], dtype=np.int16),
+        imp=np.array(rec["imp"], dtype=np.uint8),
+    )
+    if injected:
+        out.update(reset_words0=w0, step_words=np.array(rec["step_words"]), reset_words=np.array(rec["reset_words"]),
+                   act_words=np.array(rec["act_words"]))
+    return out, ref.envs[0]
+
+
+def features(name, env, flat):
+    cfg = CASES[name]
+    out = dict(case=name, flat=flat.astype(np.int16))
+    if name in GLOBAL_CASES:
+        sp, ns = reference_features(env, "global", flat)
+        for k in range(1, sp.shape[0]):
+            assert np.array_equal(sp[0], sp[k])
+        out["global_spatial"] = sp[0].astype(np.uint8)  # exact 0/1 planes
+        assert np.array_equal(out["global_spatial"].astype(np.float32), sp[0])
+        out["global_non_spatial"] = ns
+        sp, ns = reference_features(env, "perspective", flat)
+        out["perspective_spatial"] = sp.astype(np.uint8)
+        assert np.array_equal(out["perspective_spatial"].astype(np.float32), sp)
+        out["perspective_non_spatial"] = ns
+    for i, comps in enumerate(FLAT_COMPONENT_SETS.get(name, [])):
+        _, ns = reference_features(env, "flat", flat, comps)
+        out[f"flat{i}_components"] = np.array(comps)
+        out[f"flat{i}"] = ns[0]
+    del cfg
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name in CASES:
+        for injected in (False, True):
+            tr, env = trajectory(name, injected)
+            path = os.path.join(OUT, f"{name}.{'words' if injected else 'philox'}.npz")
+            np.savez_compressed(path, **tr)
+            eps = int(((tr["done"] | tr["trunc"]) != 0).sum())
+            print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB, {eps} finished episodes")
+            if not injected:
+                flat = np.concatenate([tr["next_flat"][::8].reshape(-1, tr["next_flat"].shape[-1]),
+                                       tr["reset_flat"]]).astype(np.int64)
+                ft = features(name, env, flat)
+                if len(ft) > 2:
+                    fpath = os.path.join(OUT, f"{name}.features.npz")
+                    np.savez_compressed(fpath, **ft)
+                    print(f"{fpath}: {os.path.getsize(fpath) / 1024:.1f} KiB, {flat.shape[0]} states")
+
+
+if __name__ == "__main__":
+    main()
