@@ -140,8 +140,9 @@ class OracleEnv:
         lib().orc_reset(self._h, _p(m))
         return self.flat_states()
 
-    def flat_states(self):
-        out = np.zeros((self.N, self.S), dtype=np.int64)
+    def flat_states(self, out=None):
+        if out is None:
+            out = np.zeros((self.N, self.S), dtype=np.int64)
         lib().orc_export_flat(self._h, _p(out))
         return out
 
@@ -160,8 +161,9 @@ class OracleEnv:
         lib().orc_stats(self._h, _p(out))
         return out
 
-    def sample_actions(self):
-        out = np.zeros((self.N, self.A), dtype=np.int32)
+    def sample_actions(self, out=None):
+        if out is None:
+            out = np.zeros((self.N, self.A), dtype=np.int32)
         lib().orc_sample_actions(self._h, _p(out))
         return out
 
@@ -171,15 +173,20 @@ class OracleEnv:
         tt = None if t is None else np.ascontiguousarray(t, dtype=np.int32)
         lib().orc_import_flat(self._h, _p(f), _p(m), _p(tt))
 
-    def step(self, actions=None, want_flat=True, want_metrics=True):
-        """-> dict(rewards f64 (N,A), done, trunc, next_flat (pre-reset), metrics (pre-reset), actions)."""
+    def step(self, actions=None, want_flat=True, want_metrics=True, out=None):
+        """-> dict(rewards f64 (N,A), done, trunc, next_flat (pre-reset), metrics (pre-reset), actions).
+        `out`: a dict returned by an earlier call, whose buffers are reused (timing loops)."""
         a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
-        a_out = np.zeros((self.N, self.A), dtype=np.int32)
-        rewards = np.zeros((self.N, self.A), dtype=np.float64)
-        done = np.zeros(self.N, dtype=np.uint8)
-        trunc = np.zeros(self.N, dtype=np.uint8)
-        nf = np.zeros((self.N, self.S), dtype=np.int64) if want_flat else None
-        met = np.zeros((self.N, N_METRICS), dtype=np.int64) if want_metrics else None
+        if out is not None:
+            a_out, rewards, done, trunc, nf, met = (out["actions"], out["rewards"], out["done"], out["trunc"],
+                                                    out["next_flat"], out["metrics"])
+        else:
+            a_out = np.zeros((self.N, self.A), dtype=np.int32)
+            rewards = np.zeros((self.N, self.A), dtype=np.float64)
+            done = np.zeros(self.N, dtype=np.uint8)
+            trunc = np.zeros(self.N, dtype=np.uint8)
+            nf = np.zeros((self.N, self.S), dtype=np.int64) if want_flat else None
+            met = np.zeros((self.N, N_METRICS), dtype=np.int64) if want_metrics else None
         rc = lib().orc_step(self._h, _p(a), _p(a_out), _p(rewards), _p(done), _p(trunc), _p(nf), _p(met))
         if rc != 0:
             raise IndexError("invalid action index for an agent's role list")
@@ -194,14 +201,17 @@ def n_role_actions(cfg, is_imposter):
     return lib().orc_n_role_actions(C.byref(_cfg_struct(cfg)), int(is_imposter))
 
 
-def encode_global(cfg, flat):
-    """flat (n, S) ints -> spatial (n, A+2, 9, 9) f32, non_spatial (A, n, F) f32."""
+def encode_global(cfg, flat, out=None):
+    """flat (n, S) ints -> spatial (n, A+2, 9, 9) f32, non_spatial (A, n, F) f32.  `out` = (sp, ns) to reuse."""
     c = _cfg_struct(cfg)
     f = np.ascontiguousarray(flat, dtype=np.int64)
     n, A = f.shape[0], cfg["n_imposters"] + cfg["n_crew"]
     F = lib().orc_global_nonspatial_size(C.byref(c))
-    sp = np.zeros((n, A + 2, 9, 9), dtype=np.float32)
-    ns = np.zeros((A, n, F), dtype=np.float32)
+    if out is not None:
+        sp, ns = out
+    else:
+        sp = np.zeros((n, A + 2, 9, 9), dtype=np.float32)
+        ns = np.zeros((A, n, F), dtype=np.float32)
     if lib().orc_encode_global(C.byref(c), _p(f), n, _p(sp), _p(ns)) != 0:
         raise IndexError("GlobalFeaturizer needs n_jobs > 0")
     return sp, ns

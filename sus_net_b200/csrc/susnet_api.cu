@@ -577,7 +577,7 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   p.c = e->dc;
   if (int rc = make_dev_encode(e->cfg, io->encode, p.enc, nullptr)) return rc;
   const bool enc = p.enc.kind != SUS_ENCODE_NONE;
-  if (enc && (!io->non_spatial || (p.enc.sp_floats > 0 && !io->spatial)))
+  if (enc && e->N > 0 && (!io->non_spatial || (p.enc.sp_floats > 0 && !io->spatial)))
     return fail(SUS_ERR_INVALID_ARGUMENT, "fused encode requested without output tensors");
   p.st = e->st;
   p.actions = io->actions; p.actions_dtype = io->actions_dtype; p.rewards = io->rewards; p.rewards_dtype = io->rewards_dtype;
@@ -615,7 +615,9 @@ int sus_env_check_actions(sus_env_t e, void* stream) {
 }
 
 int sus_env_sample_actions(sus_env_t e, int32_t* out, void* stream) {
-  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (e->N == 0) { e->act_epoch++; e->inj_act = nullptr; return SUS_OK; }
+  if (!out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   DeviceGuard g(e->device);
   ActParams p;
   p.c = e->dc; p.st = e->st; p.out = out; p.inj_act = e->inj_act; p.tick = e->act_epoch++; p.N = e->N;
@@ -626,7 +628,9 @@ int sus_env_sample_actions(sus_env_t e, int32_t* out, void* stream) {
 }
 
 int sus_env_export_flat(sus_env_t e, int32_t dtype, void* out, void* stream) {
-  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (e->N == 0) return SUS_OK;
+  if (!out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   DeviceGuard g(e->device);
   ExportParams p;
   p.c = e->dc; p.st = e->st; p.out = out; p.N = e->N;
@@ -640,7 +644,9 @@ int sus_env_export_flat(sus_env_t e, int32_t dtype, void* out, void* stream) {
 }
 
 int sus_env_import_flat(sus_env_t e, const int64_t* flat, const uint8_t* imposter_mask, const int32_t* t, void* stream) {
-  if (!e || !flat || !imposter_mask) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (e->N == 0) return SUS_OK;
+  if (!flat || !imposter_mask) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   DeviceGuard g(e->device);
   ImportParams p;
   p.c = e->dc; p.st = e->st; p.flat = reinterpret_cast<const long long*>(flat); p.imp = imposter_mask; p.t = t; p.N = e->N;
@@ -650,7 +656,9 @@ int sus_env_import_flat(sus_env_t e, const int64_t* flat, const uint8_t* imposte
 }
 
 int sus_env_export_imposter_mask(sus_env_t e, uint8_t* out, void* stream) {
-  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (e->N == 0) return SUS_OK;
+  if (!out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   DeviceGuard g(e->device);
   ExportParams p;
   p.c = e->dc; p.st = e->st; p.out = out; p.N = e->N;
@@ -660,7 +668,9 @@ int sus_env_export_imposter_mask(sus_env_t e, uint8_t* out, void* stream) {
 }
 
 int sus_env_export_metrics(sus_env_t e, int64_t* out, void* stream) {
-  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (e->N == 0) return SUS_OK;
+  if (!out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   DeviceGuard g(e->device);
   ExportParams p;
   p.c = e->dc; p.st = e->st; p.out = out; p.N = e->N;
@@ -677,6 +687,7 @@ int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float
   p.c = e->dc;
   if (int rc = make_dev_encode(e->cfg, spec, p.enc, nullptr)) return rc;
   if (p.enc.kind == SUS_ENCODE_NONE) return fail(SUS_ERR_INVALID_ARGUMENT, "encode kind is NONE");
+  if (e->N == 0) return SUS_OK;
   if (!non_spatial || (p.enc.sp_floats > 0 && !spatial)) return fail(SUS_ERR_INVALID_ARGUMENT, "missing output tensor");
   p.st = e->st; p.spatial = spatial; p.non_spatial = non_spatial; p.n_items = e->N;
   if (e->N == 0) return SUS_OK;
@@ -686,8 +697,9 @@ int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float
 
 int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const void* states, int32_t dtype,
                          int64_t n_items, float* spatial, float* non_spatial, int device, void* stream) {
-  if (!cfg || !spec || !states) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!cfg || !spec) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   if (int rc = validate_config(*cfg)) return rc;
+  if (n_items > 0 && !states) return fail(SUS_ERR_INVALID_ARGUMENT, "states is NULL");
   if (n_items < 0) return fail(SUS_ERR_INVALID_ARGUMENT, "n_items < 0");
   DeviceGuard g(device);
   if (!g.ok) return fail(SUS_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
@@ -696,6 +708,7 @@ int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const 
   make_dev_config(*cfg, p.c);
   if (int rc = make_dev_encode(*cfg, spec, p.enc, nullptr)) return rc;
   if (p.enc.kind == SUS_ENCODE_NONE) return fail(SUS_ERR_INVALID_ARGUMENT, "encode kind is NONE");
+  if (n_items == 0) return SUS_OK;
   if (!non_spatial || (p.enc.sp_floats > 0 && !spatial)) return fail(SUS_ERR_INVALID_ARGUMENT, "missing output tensor");
   p.rows = states; p.spatial = spatial; p.non_spatial = non_spatial; p.n_items = n_items;
   if (n_items == 0) return SUS_OK;
