@@ -156,8 +156,8 @@ class BatchedFourRoomEnv:
         N, A, S, dev = self.num_envs, self.n_agents, self._S, self.device
         self._actions = torch.zeros((N, A), dtype=torch.int32, device=dev)
         self._rewards = torch.zeros((N, A), dtype=torch.float32 if self.batched else torch.float64, device=dev)
-        self._done = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self._trunc = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._done = torch.zeros(N, dtype=torch.bool, device=dev)  # the kernel writes 0/1 bytes
+        self._trunc = torch.zeros(N, dtype=torch.bool, device=dev)
         self._next_flat = torch.zeros((N, S), dtype=torch.float32, device=dev)
         self._metrics_buf = torch.zeros((N, L.N_METRICS), dtype=torch.int64, device=dev) if not self.batched else None
         self._host_state = None  # reference mode: numpy mirror of the single env
@@ -444,7 +444,7 @@ class BatchedFourRoomEnv:
         if check if check is not None else not self.batched:
             L.check(self.lib.sus_env_check_actions(self._h, self._stream()))
         if self.batched:
-            return self._next_flat, self._rewards, self._done.bool(), self._trunc.bool(), {}
+            return self._next_flat, self._rewards, self._done, self._trunc, {}
         self._sync_host()
         rewards = self._rewards[0].cpu().numpy().copy()
         return (self._full_state_tuple(), rewards, bool(self._done[0].item()), bool(self._trunc[0].item()),
