@@ -210,7 +210,9 @@ def run_b200_arm(args):
     lib = S.lib()
 
     def make_env():
-        return S.BatchedFourRoomEnv(1, 4, 5, num_envs=N, seed=seed, env_id_base=rank * N, device=dev)
+        env = S.BatchedFourRoomEnv(1, 4, 5, num_envs=N, seed=seed, env_id_base=rank * N, device=dev)
+        env.emit_next_states = False  # the observation IS the feature tensors; raw replay rows are a separate option
+        return env
 
     def barrier():
         torch.cuda.synchronize(dev)

@@ -11,11 +11,13 @@
 //   plus small export / import kernels for the reference's flatten order.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
 #include "susnet_device.cuh"
 #include "susnet_encode.cuh"
+#include "susnet_tile.cuh"
 
 using namespace susnet;
 
@@ -137,72 +139,73 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ Rese
   store_state(p.st, e, s, true);
 }
 
-template <int VARIANT, bool ENCODE>
-__global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepParams p) {
-  __shared__ GridTables tb;
-  stage_tables(p.c, tb);
+// ---- the step of one env, shared by the direct-store kernel (k_step) and the TMA-staged kernel (k_step_tma).
+// rew_row / nf_row point at THIS env's reward / next_flat row: in global memory (direct) or in the warp's
+// shared-memory staging block (TMA path).
+template <int VARIANT>
+__device__ __forceinline__ void step_one(const StepParams& p, const GridTables& tb, int64_t e, bool have, void* rew_row,
+                                         float* nf_row, EnvState& s, StepResult& r, bool& stepped, bool& finished) {
   const DevConfig& c = p.c;
   const int A = c.A;
-  const int lane = threadIdx.x & 31;
-  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const int64_t e0 = e - lane;
-  const bool have = e < p.N;
-  bool stepped = false, finished = false;
-  EnvState s = {};
-  StepResult r = {};
-  if (have) {
-    load_state(p.st, e, s);
-    // ---- actions: role-list indices, one byte per agent
-    uint64_t acts = 0;
-    bool ok = true;
-    if (p.actions == nullptr) {  // fused random policy == env.step(env.sample_actions()), base.py:326-330
-      WordStream wa;
-      wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, p.tick, P_ACT_FUSED);
-      for (int i = 0; i < A; ++i)
-        acts |= (uint64_t)bounded(wa.word(i), n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) << (8 * i);
-    } else {
-      for (int i = 0; i < A; ++i) {
-        long long a;
-        if (p.actions_dtype == SUS_I32) a = static_cast<const int32_t*>(p.actions)[e * A + i];
-        else if (p.actions_dtype == SUS_I64) a = static_cast<const long long*>(p.actions)[e * A + i];
-        else a = static_cast<const uint8_t*>(p.actions)[e * A + i];
-        if (a < 0 || a >= (long long)n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) { ok = false; a = 0; }
-        acts |= (uint64_t)a << (8 * i);
-      }
-    }
-    if (p.actions_out)
-      for (int i = 0; i < A; ++i) p.actions_out[e * A + i] = (int32_t)get_byte(acts, i);
-    if (ok) {
-      WordStream ws;
-      ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, p.tick, P_STEP);
-      step_env<VARIANT>(c, tb, s, acts, ws, r);
-      stepped = true;
-      finished = r.done || r.trunc;
-      if (p.rewards) {
-        if (p.rewards_dtype == SUS_F64) {
-          double* o = static_cast<double*>(p.rewards) + e * A;
-          for (int i = 0; i < A; ++i) o[i] = agent_reward<VARIANT>(c, s, r, i);
-        } else {
-          float* o = static_cast<float*>(p.rewards) + e * A;
-          for (int i = 0; i < A; ++i) o[i] = (float)agent_reward<VARIANT>(c, s, r, i);
-        }
-      }
-      if (p.done) p.done[e] = r.done;
-      if (p.trunc) p.trunc[e] = r.trunc;
-      if (p.next_flat) write_flat<float>(c, s, p.next_flat + e * c.S);
-      if (p.metrics) {
-        long long* m = p.metrics + e * SUS_N_METRICS;
-        m[SUS_M_TOTAL_TIME_STEPS] = s.nsteps; m[SUS_M_IMP_KILLED_CREW] = s.misc & 0xff;
-        m[SUS_M_COMPLETED_JOBS] = s.completed; m[SUS_M_SABOTAGED_JOBS] = s.sabotaged;
-        m[SUS_M_IMP_VOTED_OUT] = (s.misc >> 8) & 0xff; m[SUS_M_CREW_VOTED_OUT] = (s.misc >> 16) & 0xff;
-        m[SUS_M_CREW_WON] = (s.misc >> 24) & 1u; m[SUS_M_IMPOSTER_WON] = (s.misc >> 25) & 1u;
-      }
-    } else {
-      atomicAdd(p.err, 1u);
+  stepped = false;
+  finished = false;
+  if (!have) return;
+  load_state(p.st, e, s);
+  // ---- actions: role-list indices, one byte per agent
+  uint64_t acts = 0;
+  bool ok = true;
+  if (p.actions == nullptr) {  // fused random policy == env.step(env.sample_actions()), base.py:326-330
+    WordStream wa;
+    wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, p.tick, P_ACT_FUSED);
+    for (int i = 0; i < A; ++i)
+      acts |= (uint64_t)bounded(wa.word(i), n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) << (8 * i);
+  } else {
+    for (int i = 0; i < A; ++i) {
+      long long a;
+      if (p.actions_dtype == SUS_I32) a = static_cast<const int32_t*>(p.actions)[e * A + i];
+      else if (p.actions_dtype == SUS_I64) a = static_cast<const long long*>(p.actions)[e * A + i];
+      else a = static_cast<const uint8_t*>(p.actions)[e * A + i];
+      if (a < 0 || a >= (long long)n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) { ok = false; a = 0; }
+      acts |= (uint64_t)a << (8 * i);
     }
   }
-  // ---- finished-episode statistics: warp reduction, one atomic per statistic per warp
-  if (__any_sync(kFull, finished)) {
+  if (p.actions_out)
+    for (int i = 0; i < A; ++i) p.actions_out[e * A + i] = (int32_t)get_byte(acts, i);
+  if (!ok) {  // reference: IndexError (base.py:381); here the env is left untouched and the error is counted
+    atomicAdd(p.err, 1u);
+    return;
+  }
+  WordStream ws;
+  ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, p.tick, P_STEP);
+  step_env<VARIANT>(c, tb, s, acts, ws, r);
+  stepped = true;
+  finished = r.done || r.trunc;
+  if (rew_row) {
+    if (p.rewards_dtype == SUS_F64) {
+      double* o = static_cast<double*>(rew_row);
+      for (int i = 0; i < A; ++i) o[i] = agent_reward<VARIANT>(c, s, r, i);
+    } else {
+      float* o = static_cast<float*>(rew_row);
+      for (int i = 0; i < A; ++i) o[i] = (float)agent_reward<VARIANT>(c, s, r, i);
+    }
+  }
+  if (p.done) p.done[e] = r.done;
+  if (p.trunc) p.trunc[e] = r.trunc;
+  if (nf_row) write_flat<float>(c, s, nf_row);
+  if (p.metrics) {
+    long long* m = p.metrics + e * SUS_N_METRICS;
+    m[SUS_M_TOTAL_TIME_STEPS] = s.nsteps; m[SUS_M_IMP_KILLED_CREW] = s.misc & 0xff;
+    m[SUS_M_COMPLETED_JOBS] = s.completed; m[SUS_M_SABOTAGED_JOBS] = s.sabotaged;
+    m[SUS_M_IMP_VOTED_OUT] = (s.misc >> 8) & 0xff; m[SUS_M_CREW_VOTED_OUT] = (s.misc >> 16) & 0xff;
+    m[SUS_M_CREW_WON] = (s.misc >> 24) & 1u; m[SUS_M_IMPOSTER_WON] = (s.misc >> 25) & 1u;
+  }
+}
+
+// ---- episode statistics, auto-reset and state write-back; all 32 lanes of the warp must call this together
+__device__ __forceinline__ void finish_one(const StepParams& p, const GridTables& tb, int64_t e, int lane, EnvState& s,
+                                           const StepResult& r, bool stepped, bool finished) {
+  const DevConfig& c = p.c;
+  if (__any_sync(kFull, finished)) {  // warp reduction, one atomic per statistic per warp
     const uint32_t f = finished ? 1u : 0u;
     uint32_t v[SUS_N_STATS];
     v[SUS_S_EPISODES] = f; v[SUS_S_CREW_WON] = f * ((s.misc >> 24) & 1u); v[SUS_S_IMPOSTER_WON] = f * ((s.misc >> 25) & 1u);
@@ -220,17 +223,91 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepP
   if (stepped) {
     if (finished && c.auto_reset) {  // SURVEY.md A.7; train.py:419-445 does this on the host
       WordStream wr;
-      wr.init(c, p.inj_reset ? p.inj_reset + e * (c.nI + A + c.J) : nullptr, (uint32_t)e, p.tick, P_AUTORESET);
+      wr.init(c, p.inj_reset ? p.inj_reset + e * (c.nI + c.A + c.J) : nullptr, (uint32_t)e, p.tick, P_AUTORESET);
       reset_env(c, tb, s, wr);
       store_state(p.st, e, s, true);
     } else {
       store_state(p.st, e, s, false);
     }
   }
+}
+
+// K1 (+K2), direct-store path: one thread per env, outputs written straight from registers.  Used for ragged or
+// unaligned outputs and as the fallback when the staging tiles do not fit in shared memory.
+template <int VARIANT, bool ENCODE>
+__global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepParams p) {
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t e0 = e - lane;
+  const bool have = e < p.N;
+  bool stepped, finished;
+  EnvState s = {};
+  StepResult r = {};
+  step_one<VARIANT>(p, tb, e, have,
+                    p.rewards ? static_cast<uint8_t*>(p.rewards) + e * p.c.A * (p.rewards_dtype == SUS_F64 ? 8 : 4) : nullptr,
+                    p.next_flat ? p.next_flat + e * p.c.S : nullptr, s, r, stepped, finished);
+  finish_one(p, tb, e, lane, s, r, stepped, finished);
   if (ENCODE) {
     const int64_t rem = p.N - e0;
-    warp_encode(c, p.enc, tb, obs_of(s), e0, rem < 32 ? (int)(rem < 0 ? 0 : rem) : 32, have, p.N, p.spatial, p.non_spatial);
+    warp_encode(p.c, p.enc, tb, obs_of(s), e0, rem < 32 ? (int)(rem < 0 ? 0 : rem) : 32, have, p.N, p.spatial, p.non_spatial);
   }
+}
+
+// K1 (+K2), TMA path: persistent CTAs (one per SM), each warp walks groups of 32 envs; rewards, the replay-layout
+// state row and the feature tensors are staged in shared memory and leave the SM as TMA bulk stores.
+template <int VARIANT, bool ENCODE>
+__global__ void __launch_bounds__(kThreads, 1) k_step_tma(const __grid_constant__ StepParams p,
+                                                          const __grid_constant__ TileLayout L) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int A = p.c.A;
+  WarpEmitter em{dyn_smem + (size_t)warp * L.per_warp, &L, lane, false};
+  if (ENCODE && p.enc.sp_floats > 0) em.zero_spatial();
+  const int64_t n_groups = (p.N + 31) >> 5;
+  const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
+  for (int64_t g = (int64_t)blockIdx.x * L.warps + warp; g < n_groups; g += (int64_t)gridDim.x * L.warps) {
+    const int64_t e0 = g << 5, e = e0 + lane;
+    const bool have = e < p.N;
+    const int64_t rem = p.N - e0;
+    const int cnt = rem < 32 ? (int)rem : 32;
+    bool stepped, finished;
+    EnvState s = {};
+    StepResult r = {};
+    em.acquire();  // the previous group's bulk stores have finished reading the staging block
+    step_one<VARIANT>(p, tb, e, have, p.rewards ? em.rew() + lane * A * rew_elem : nullptr,
+                      p.next_flat ? em.nf() + lane * p.c.S : nullptr, s, r, stepped, finished);
+    finish_one(p, tb, e, lane, s, r, stepped, finished);
+    // an env whose actions were rejected keeps its old outputs: do not publish the stale staging rows
+    const bool all_stepped = __all_sync(kFull, stepped || !have);
+    if (p.rewards || p.next_flat) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      bool any = false;
+      if (all_stepped) {
+        if (p.rewards)
+          any |= drain(static_cast<uint8_t*>(p.rewards) + e0 * A * rew_elem, em.rew(), (uint32_t)(cnt * A * rew_elem), lane);
+        if (p.next_flat) any |= drain(p.next_flat + e0 * p.c.S, em.nf(), (uint32_t)(cnt * p.c.S * 4), lane);
+      } else if (stepped) {  // rare: publish row by row from the lanes that did step
+        if (p.rewards) {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(em.rew() + lane * A * rew_elem);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.rewards) + e * A * rew_elem);
+          for (int i = 0; i < A * rew_elem / 4; ++i) dst[i] = src[i];
+        }
+        if (p.next_flat)
+          for (int i = 0; i < p.c.S; ++i) p.next_flat[e * p.c.S + i] = em.nf()[lane * p.c.S + i];
+      }
+      if (any) {
+        if (lane == 0) bulk_commit();
+        em.pending = true;
+      }
+    }
+    if (ENCODE) warp_encode_tma(p.c, p.enc, tb, em, obs_of(s), e0, cnt, have, p.N, p.spatial, p.non_spatial, true);
+  }
+  em.finish();
 }
 
 __global__ void __launch_bounds__(kThreads) k_sample_actions(const __grid_constant__ ActParams p) {
@@ -300,6 +377,36 @@ __global__ void __launch_bounds__(kThreads) k_encode_rows(const __grid_constant_
   if (have) o = parse_row<T>(p.c, static_cast<const T*>(p.rows) + e * p.c.S);
   const int64_t rem = p.n_items - e0;
   warp_encode(p.c, p.enc, tb, o, e0, rem < 32 ? (int)(rem < 0 ? 0 : rem) : 32, have, p.n_items, p.spatial, p.non_spatial);
+}
+
+// K2, TMA path (see k_step_tma): persistent CTAs, features staged in shared memory, bulk stores.
+template <typename T, bool FROM_ROWS>
+__global__ void __launch_bounds__(kThreads, 1) k_encode_tma(const __grid_constant__ EncodeParams p,
+                                                            const __grid_constant__ TileLayout L) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpEmitter em{dyn_smem + (size_t)warp * L.per_warp, &L, lane, false};
+  if (p.enc.sp_floats > 0) em.zero_spatial();
+  const int64_t n_groups = (p.n_items + 31) >> 5;
+  for (int64_t g = (int64_t)blockIdx.x * L.warps + warp; g < n_groups; g += (int64_t)gridDim.x * L.warps) {
+    const int64_t e0 = g << 5, e = e0 + lane;
+    const bool have = e < p.n_items;
+    const int64_t rem = p.n_items - e0;
+    ObsState o = {};
+    if (have) {
+      if (FROM_ROWS) {
+        o = parse_row<T>(p.c, static_cast<const T*>(p.rows) + e * p.c.S);
+      } else {
+        EnvState s;
+        load_state(p.st, e, s);
+        o = obs_of(s);
+      }
+    }
+    warp_encode_tma(p.c, p.enc, tb, em, o, e0, rem < 32 ? (int)rem : 32, have, p.n_items, p.spatial, p.non_spatial, false);
+  }
+  em.finish();
 }
 
 template <typename T>
@@ -459,6 +566,65 @@ int make_dev_encode(const SusConfig& c, const SusEncodeSpec* spec, DevEncode& d,
   return SUS_OK;
 }
 
+inline int32_t align128(int64_t b) { return (int32_t)((b + 127) & ~127ll); }
+
+struct DeviceInfo {
+  int sms = 0;
+  int max_dyn_smem = 0;
+};
+
+int device_info(int device, DeviceInfo& d) {
+  static DeviceInfo cache[64];
+  static bool have[64] = {};
+  if (device >= 0 && device < 64 && have[device]) { d = cache[device]; return SUS_OK; }
+  SUS_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device));
+  SUS_CUDA(cudaDeviceGetAttribute(&d.max_dyn_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if (device >= 0 && device < 64) { cache[device] = d; have[device] = true; }
+  return SUS_OK;
+}
+
+// SUSNET_PATH=direct forces the register/LSU store path, SUSNET_PATH=tma (default) the shared-memory + TMA path.
+bool want_tma() {
+  const char* v = std::getenv("SUSNET_PATH");
+  return !(v && std::strcmp(v, "direct") == 0);
+}
+
+// Per-warp staging layout; returns false if not even two warps fit (then the direct path is used).
+bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, TileLayout& L) {
+  const int views = enc.kind == SUS_ENCODE_NONE ? 0 : (enc.kind == SUS_ENCODE_FLAT ? 1 : c.A);
+  TileLayout best = {};
+  for (int G : {8, 4}) {
+    TileLayout t = {};
+    t.G = G;
+    int off = 0;
+    t.sp_off = off; t.sp_bytes = align128((int64_t)G * enc.sp_floats * 4); off += t.sp_bytes;
+    t.ns_off = off; t.ns_bytes = align128((int64_t)views * 32 * enc.ns_floats * 4); off += t.ns_bytes;
+    t.rew_off = off; t.rew_bytes = align128((int64_t)32 * c.A * rew_elem); off += t.rew_bytes;
+    t.nf_off = off; t.nf_bytes = want_nf ? align128((int64_t)32 * c.S * 4) : 0; off += t.nf_bytes;
+    t.per_warp = off > 0 ? off : 128;
+    const int budget = max_dyn_smem - 2048;  // static tables + slack
+    t.warps = budget / t.per_warp;
+    if (t.warps > kThreads / 32) t.warps = kThreads / 32;
+    if (t.warps > best.warps) best = t;
+    if (best.warps == kThreads / 32) break;
+  }
+  if (best.warps < 2) return false;
+  L = best;
+  return true;
+}
+
+unsigned persistent_grid(int64_t n_items, const TileLayout& L, int sms) {
+  const int64_t groups = (n_items + 31) / 32;
+  const int64_t ctas = (groups + L.warps - 1) / L.warps;
+  return (unsigned)(ctas < sms ? ctas : sms);
+}
+
+template <typename K>
+int allow_big_smem(K kernel, size_t bytes) {
+  SUS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return SUS_OK;
+}
+
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 int after_launch(const char* what) {
@@ -587,8 +753,32 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   p.stats = e->stats; p.err = e->err; p.tick = e->step_tick++; p.N = e->N;
   e->inj_step = e->inj_reset = e->inj_act = nullptr;
   if (e->N == 0) return SUS_OK;
-  const unsigned gr = grid_for(e->N);
   cudaStream_t st = (cudaStream_t)stream;
+  DeviceInfo di;
+  if (int rc = device_info(e->device, di)) return rc;
+  TileLayout L;
+  const bool staged_outputs = enc || io->rewards || io->next_flat;
+  if (want_tma() && staged_outputs &&
+      make_layout(p.c, p.enc, io->rewards_dtype == SUS_F64 ? 8 : 4, io->next_flat != nullptr, di.max_dyn_smem, L)) {
+    const size_t smem = (size_t)L.per_warp * L.warps;
+    const unsigned gr = persistent_grid(e->N, L, di.sms);
+#define SUS_LAUNCH_STEP_TMA(V)                                                        \
+  if (enc) {                                                                          \
+    if (int rc = allow_big_smem(k_step_tma<V, true>, smem)) return rc;                \
+    k_step_tma<V, true><<<gr, L.warps * 32, smem, st>>>(p, L);                        \
+  } else {                                                                            \
+    if (int rc = allow_big_smem(k_step_tma<V, false>, smem)) return rc;               \
+    k_step_tma<V, false><<<gr, L.warps * 32, smem, st>>>(p, L);                       \
+  }
+    switch (e->cfg.variant) {
+      case SUS_VARIANT_BASE: SUS_LAUNCH_STEP_TMA(SUS_VARIANT_BASE); break;
+      case SUS_VARIANT_TAGGING: SUS_LAUNCH_STEP_TMA(SUS_VARIANT_TAGGING); break;
+      default: SUS_LAUNCH_STEP_TMA(SUS_VARIANT_TRAINING_GROUND); break;
+    }
+#undef SUS_LAUNCH_STEP_TMA
+    return after_launch("k_step_tma");
+  }
+  const unsigned gr = grid_for(e->N);
 #define SUS_LAUNCH_STEP(V)                                      \
   if (enc) k_step<V, true><<<gr, kThreads, 0, st>>>(p);         \
   else k_step<V, false><<<gr, kThreads, 0, st>>>(p)
@@ -691,6 +881,15 @@ int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float
   if (!non_spatial || (p.enc.sp_floats > 0 && !spatial)) return fail(SUS_ERR_INVALID_ARGUMENT, "missing output tensor");
   p.st = e->st; p.spatial = spatial; p.non_spatial = non_spatial; p.n_items = e->N;
   if (e->N == 0) return SUS_OK;
+  DeviceInfo di;
+  if (int rc = device_info(e->device, di)) return rc;
+  TileLayout L;
+  if (want_tma() && make_layout(p.c, p.enc, 0, false, di.max_dyn_smem, L)) {
+    const size_t smem = (size_t)L.per_warp * L.warps;
+    if (int rc = allow_big_smem(k_encode_tma<float, false>, smem)) return rc;
+    k_encode_tma<float, false><<<persistent_grid(e->N, L, di.sms), L.warps * 32, smem, (cudaStream_t)stream>>>(p, L);
+    return after_launch("k_encode_tma");
+  }
   k_encode_env<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
   return after_launch("k_encode_env");
 }
@@ -713,10 +912,29 @@ int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const 
   p.rows = states; p.spatial = spatial; p.non_spatial = non_spatial; p.n_items = n_items;
   if (n_items == 0) return SUS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype != SUS_F32 && dtype != SUS_F64 && dtype != SUS_I64)
+    return fail(SUS_ERR_INVALID_ARGUMENT, "states dtype must be SUS_F32, SUS_F64 or SUS_I64");
+  DeviceInfo di;
+  if (int rc = device_info(device, di)) return rc;
+  TileLayout L;
+  if (want_tma() && make_layout(p.c, p.enc, 0, false, di.max_dyn_smem, L)) {
+    const size_t smem = (size_t)L.per_warp * L.warps;
+    const unsigned gr = persistent_grid(n_items, L, di.sms);
+    if (dtype == SUS_F32) {
+      if (int rc = allow_big_smem(k_encode_tma<float, true>, smem)) return rc;
+      k_encode_tma<float, true><<<gr, L.warps * 32, smem, st>>>(p, L);
+    } else if (dtype == SUS_F64) {
+      if (int rc = allow_big_smem(k_encode_tma<double, true>, smem)) return rc;
+      k_encode_tma<double, true><<<gr, L.warps * 32, smem, st>>>(p, L);
+    } else {
+      if (int rc = allow_big_smem(k_encode_tma<long long, true>, smem)) return rc;
+      k_encode_tma<long long, true><<<gr, L.warps * 32, smem, st>>>(p, L);
+    }
+    return after_launch("k_encode_tma");
+  }
   if (dtype == SUS_F32) k_encode_rows<float><<<grid_for(n_items), kThreads, 0, st>>>(p);
   else if (dtype == SUS_F64) k_encode_rows<double><<<grid_for(n_items), kThreads, 0, st>>>(p);
-  else if (dtype == SUS_I64) k_encode_rows<long long><<<grid_for(n_items), kThreads, 0, st>>>(p);
-  else return fail(SUS_ERR_INVALID_ARGUMENT, "states dtype must be SUS_F32, SUS_F64 or SUS_I64");
+  else k_encode_rows<long long><<<grid_for(n_items), kThreads, 0, st>>>(p);
   return after_launch("k_encode_rows");
 }
 

@@ -37,15 +37,15 @@ __device__ __forceinline__ bool code_ok(uint32_t c) { return (c >> 4) <= 8u && (
 // (AgentPositionsFeaturizer component.py:90-100, JobFeaturizer component.py:116-127).
 template <typename ChannelOf>
 __device__ __forceinline__ void scatter_planes(const DevConfig& c, const ObsState& o, float* __restrict__ sp,
-                                               ChannelOf ch_of) {
+                                               ChannelOf ch_of, float v) {
   const int A = c.A, J = c.J;
   for (int i = 0; i < A; ++i) {
     const uint32_t b = get_byte(o.pos, i);
-    if (((o.alive >> i) & 1u) && code_ok(b)) sp[ch_of(i) * 81 + code_cell(b)] = 1.0f;
+    if (((o.alive >> i) & 1u) && code_ok(b)) sp[ch_of(i) * 81 + code_cell(b)] = v;
   }
   for (int j = 0; j < J; ++j) {
     const uint32_t b = get_byte(o.jobpos, j);
-    if (code_ok(b)) sp[(A + (int)((o.jobdone >> j) & 1u)) * 81 + code_cell(b)] = 1.0f;
+    if (code_ok(b)) sp[(A + (int)((o.jobdone >> j) & 1u)) * 81 + code_cell(b)] = v;
   }
 }
 
@@ -187,7 +187,7 @@ __device__ __forceinline__ void warp_encode(const DevConfig& c, const DevEncode&
     warp_zero_fill(spatial + item0 * R, (int64_t)cnt * R, lane);
     __syncwarp();
     if (have) {
-      scatter_planes(c, o, spatial + item * R, [](int i) { return i; });
+      scatter_planes(c, o, spatial + item * R, [](int i) { return i; }, 1.0f);
       for (int k = 0; k < A; ++k) global_ns_row(c, o, k, non_spatial + ((int64_t)k * n_items + item) * enc.ns_floats);
     }
   } else if (enc.kind == SUS_ENCODE_PERSPECTIVE) {
@@ -197,7 +197,7 @@ __device__ __forceinline__ void warp_encode(const DevConfig& c, const DevEncode&
     if (have) {
       for (int k = 0; k < A; ++k) {
         scatter_planes(c, o, spatial + ((int64_t)k * n_items + item) * R,
-                       [k](int i) { return persp_channel_of_agent(k, i); });
+                       [k](int i) { return persp_channel_of_agent(k, i); }, 1.0f);
         persp_ns_row(c, o, k, non_spatial + ((int64_t)k * n_items + item) * enc.ns_floats);
       }
     }

@@ -160,6 +160,7 @@ class BatchedFourRoomEnv:
         self._trunc = torch.zeros(N, dtype=torch.bool, device=dev)
         self._next_flat = torch.zeros((N, S), dtype=torch.float32, device=dev)
         self._metrics_buf = torch.zeros((N, L.N_METRICS), dtype=torch.int64, device=dev) if not self.batched else None
+        self.emit_next_states = True  # batched mode: write the (N, S) replay-layout next-state rows every step
         self._host_state = None  # reference mode: numpy mirror of the single env
         self._imp_cache = None
         self._was_reset = False
@@ -431,7 +432,8 @@ class BatchedFourRoomEnv:
         io.rewards_dtype = _TORCH_TO_SUS[self._rewards.dtype]
         io.done = self._done.data_ptr()
         io.truncated = self._trunc.data_ptr()
-        io.next_flat = self._next_flat.data_ptr()
+        if self.emit_next_states:
+            io.next_flat = self._next_flat.data_ptr()
         if self._metrics_buf is not None:
             io.metrics = self._metrics_buf.data_ptr()
         spec = None
@@ -444,7 +446,7 @@ class BatchedFourRoomEnv:
         if check if check is not None else not self.batched:
             L.check(self.lib.sus_env_check_actions(self._h, self._stream()))
         if self.batched:
-            return self._next_flat, self._rewards, self._done, self._trunc, {}
+            return (self._next_flat if self.emit_next_states else None), self._rewards, self._done, self._trunc, {}
         self._sync_host()
         rewards = self._rewards[0].cpu().numpy().copy()
         return (self._full_state_tuple(), rewards, bool(self._done[0].item()), bool(self._trunc[0].item()),

@@ -13,6 +13,14 @@ from tests.util import CASES, case_of, flat_featurizer, golden_files, load, make
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["tma", "direct"], autouse=True)
+def store_path(request, monkeypatch):
+    """Every GPU test runs on both output paths of the kernels: shared-memory staging + TMA bulk stores (default)
+    and direct register stores (the fallback for ragged / unaligned outputs)."""
+    monkeypatch.setenv("SUSNET_PATH", request.param)
+    return request.param
+
+
 def cpu(t):
     return t.detach().cpu().numpy()
 
