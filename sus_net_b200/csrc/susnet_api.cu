@@ -265,7 +265,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_step_tma(const __grid_constant_
   stage_tables(p.c, tb);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int A = p.c.A;
-  WarpEmitter em{dyn_smem + (size_t)warp * L.per_warp, &L, lane, false};
+  WarpEmitter em;
+  em.init(dyn_smem + (size_t)warp * L.per_warp, &L, lane);
   if (ENCODE && p.enc.sp_floats > 0) em.zero_spatial();
   const int64_t n_groups = (p.N + 31) >> 5;
   const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
@@ -277,20 +278,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_step_tma(const __grid_constant_
     bool stepped, finished;
     EnvState s = {};
     StepResult r = {};
-    em.acquire();  // the previous group's bulk stores have finished reading the staging block
+    em.acquire_dense();  // the previous group's dense bulk stores have finished reading the staging rows
     step_one<VARIANT>(p, tb, e, have, p.rewards ? em.rew() + lane * A * rew_elem : nullptr,
                       p.next_flat ? em.nf() + lane * p.c.S : nullptr, s, r, stepped, finished);
     finish_one(p, tb, e, lane, s, r, stepped, finished);
     // an env whose actions were rejected keeps its old outputs: do not publish the stale staging rows
     const bool all_stepped = __all_sync(kFull, stepped || !have);
+    bool dense_any = false;
     if (p.rewards || p.next_flat) {
-      fence_proxy_async_smem();
-      __syncwarp();
-      bool any = false;
+      if (!ENCODE) { fence_proxy_async_smem(); __syncwarp(); }  // with ENCODE the fence before the ns drain covers these rows
+      else __syncwarp();
       if (all_stepped) {
+        if (ENCODE) { fence_proxy_async_smem(); __syncwarp(); }
         if (p.rewards)
-          any |= drain(static_cast<uint8_t*>(p.rewards) + e0 * A * rew_elem, em.rew(), (uint32_t)(cnt * A * rew_elem), lane);
-        if (p.next_flat) any |= drain(p.next_flat + e0 * p.c.S, em.nf(), (uint32_t)(cnt * p.c.S * 4), lane);
+          dense_any |= drain(static_cast<uint8_t*>(p.rewards) + e0 * A * rew_elem, em.rew(), (uint32_t)(cnt * A * rew_elem), lane);
+        if (p.next_flat) dense_any |= drain(p.next_flat + e0 * p.c.S, em.nf(), (uint32_t)(cnt * p.c.S * 4), lane);
       } else if (stepped) {  // rare: publish row by row from the lanes that did step
         if (p.rewards) {
           const uint32_t* src = reinterpret_cast<const uint32_t*>(em.rew() + lane * A * rew_elem);
@@ -300,12 +302,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_step_tma(const __grid_constant_
         if (p.next_flat)
           for (int i = 0; i < p.c.S; ++i) p.next_flat[e * p.c.S + i] = em.nf()[lane * p.c.S + i];
       }
-      if (any) {
+      if (!ENCODE && dense_any) {
         if (lane == 0) bulk_commit();
-        em.pending = true;
+        em.committed_dense();
       }
     }
-    if (ENCODE) warp_encode_tma(p.c, p.enc, tb, em, obs_of(s), e0, cnt, have, p.N, p.spatial, p.non_spatial, true);
+    if (ENCODE)
+      warp_encode_tma(p.c, p.enc, tb, em, obs_of(s), e0, cnt, have, p.N, p.spatial, p.non_spatial, true, dense_any);
   }
   em.finish();
 }
@@ -387,7 +390,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_encode_tma(const __grid_constan
   __shared__ GridTables tb;
   stage_tables(p.c, tb);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpEmitter em{dyn_smem + (size_t)warp * L.per_warp, &L, lane, false};
+  WarpEmitter em;
+  em.init(dyn_smem + (size_t)warp * L.per_warp, &L, lane);
   if (p.enc.sp_floats > 0) em.zero_spatial();
   const int64_t n_groups = (p.n_items + 31) >> 5;
   for (int64_t g = (int64_t)blockIdx.x * L.warps + warp; g < n_groups; g += (int64_t)gridDim.x * L.warps) {
@@ -404,7 +408,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_encode_tma(const __grid_constan
         o = obs_of(s);
       }
     }
-    warp_encode_tma(p.c, p.enc, tb, em, o, e0, rem < 32 ? (int)rem : 32, have, p.n_items, p.spatial, p.non_spatial, false);
+    warp_encode_tma(p.c, p.enc, tb, em, o, e0, rem < 32 ? (int)rem : 32, have, p.n_items, p.spatial, p.non_spatial, false,
+                    false);
   }
   em.finish();
 }
@@ -593,7 +598,12 @@ bool want_tma() {
 bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, TileLayout& L) {
   const int views = enc.kind == SUS_ENCODE_NONE ? 0 : (enc.kind == SUS_ENCODE_FLAT ? 1 : c.A);
   TileLayout best = {};
-  for (int G : {8, 4}) {
+  // tuning overrides (tools/kernel_sweep.py): SUSNET_TILE_G in {4, 8, 16}, SUSNET_TILE_WARPS in 2..8
+  const char* env_g = std::getenv("SUSNET_TILE_G");
+  const char* env_w = std::getenv("SUSNET_TILE_WARPS");
+  const int force_g = env_g ? std::atoi(env_g) : 0, force_w = env_w ? std::atoi(env_w) : 0;
+  for (int G : {8, 4, 16}) {
+    if (force_g ? G != force_g : G == 16) continue;
     TileLayout t = {};
     t.G = G;
     int off = 0;
@@ -605,6 +615,7 @@ bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool wa
     const int budget = max_dyn_smem - 2048;  // static tables + slack
     t.warps = budget / t.per_warp;
     if (t.warps > kThreads / 32) t.warps = kThreads / 32;
+    if (force_w > 0 && force_w < t.warps) t.warps = force_w;
     if (t.warps > best.warps) best = t;
     if (best.warps == kThreads / 32) break;
   }

@@ -49,6 +49,50 @@ __device__ __forceinline__ void scatter_planes(const DevConfig& c, const ObsStat
   }
 }
 
+// The same planes as a packed list of float offsets inside one item's (A+2)*81 row, computed once per item so that
+// setting and clearing the ones in a staging tile is a handful of shifts and stores.  Up to 16 entries of 10 bits
+// (offset < 1024 > (8+2)*81); 0x3ff marks "no entry" (dead agent, coordinate outside the grid).
+struct PlaneOffsets {
+  uint64_t w[3];  // entries 0-5, 6-11, 12-15
+  int n;
+  __device__ __forceinline__ uint32_t get(int q) const {
+    const uint64_t x = q < 6 ? w[0] : (q < 12 ? w[1] : w[2]);
+    const int sh = 10 * (q < 6 ? q : (q < 12 ? q - 6 : q - 12));
+    return (uint32_t)(x >> sh) & 0x3ffu;
+  }
+};
+
+template <typename ChannelOf>
+__device__ __forceinline__ PlaneOffsets plane_offsets(const DevConfig& c, const ObsState& o, ChannelOf ch_of) {
+  const int A = c.A, J = c.J;
+  PlaneOffsets po;
+  po.w[0] = po.w[1] = po.w[2] = 0;
+  po.n = A + J;
+  for (int q = 0; q < A + J; ++q) {
+    uint32_t off = 0x3ffu;
+    if (q < A) {
+      const uint32_t b = get_byte(o.pos, q);
+      if (((o.alive >> q) & 1u) && code_ok(b)) off = (uint32_t)ch_of(q) * 81u + code_cell(b);
+    } else {
+      const int j = q - A;
+      const uint32_t b = get_byte(o.jobpos, j);
+      if (code_ok(b)) off = (uint32_t)(A + (int)((o.jobdone >> j) & 1u)) * 81u + code_cell(b);
+    }
+    const int wi = q < 6 ? 0 : (q < 12 ? 1 : 2);
+    const int sh = 10 * (q - 6 * wi);
+    const uint64_t v = (uint64_t)off << sh;
+    if (wi == 0) po.w[0] |= v; else if (wi == 1) po.w[1] |= v; else po.w[2] |= v;
+  }
+  return po;
+}
+
+__device__ __forceinline__ void put_planes(const PlaneOffsets& po, float* __restrict__ row, float v) {
+  for (int q = 0; q < po.n; ++q) {
+    const uint32_t off = po.get(q);
+    if (off != 0x3ffu) row[off] = v;
+  }
+}
+
 // GlobalFeaturizer non-spatial row of view k: alive, [tag counts], job status, one-hot(k)
 // (model_ready.py:237-247,293-303).  Tagging fields are read in TUPLE order (documented deviation from
 // the reference's inconsistent state_fields map).
@@ -73,6 +117,28 @@ __device__ __forceinline__ void persp_ns_row(const DevConfig& c, const ObsState&
   if (c.variant == SUS_VARIANT_TAGGING)
     for (int ch = 0; ch < A; ++ch) r[p++] = (float)((o.tagcnt >> (4 * persp_agent_of_channel(k, ch))) & 15u);
   for (int j = 0; j < J; ++j) r[p++] = (float)((o.jobdone >> j) & 1u);
+}
+
+// All A view rows of one item in one pass (row k at base + k * stride): the alive / tag / job-status prefix is the
+// same in every Global view, so each value is converted once and stored A times.
+__device__ __forceinline__ void global_ns_rows(const DevConfig& c, const ObsState& o, float* __restrict__ base, int stride) {
+  const int A = c.A, J = c.J;
+  int p = 0;
+  for (int i = 0; i < A; ++i, ++p) {
+    const float v = (float)((o.alive >> i) & 1u);
+    for (int k = 0; k < A; ++k) base[k * stride + p] = v;
+  }
+  if (c.variant == SUS_VARIANT_TAGGING)
+    for (int i = 0; i < A; ++i, ++p) {
+      const float v = (float)((o.tagcnt >> (4 * i)) & 15u);
+      for (int k = 0; k < A; ++k) base[k * stride + p] = v;
+    }
+  for (int j = 0; j < J; ++j, ++p) {
+    const float v = (float)((o.jobdone >> j) & 1u);
+    for (int k = 0; k < A; ++k) base[k * stride + p] = v;
+  }
+  for (int k = 0; k < A; ++k)
+    for (int i = 0; i < A; ++i) base[k * stride + p + i] = i == k ? 1.0f : 0.0f;
 }
 
 __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }

@@ -35,6 +35,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all_but_newest() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Drain `bytes` of shared memory to global memory.  Lane 0 issues a TMA bulk store when source, destination and
@@ -54,24 +55,61 @@ __device__ __forceinline__ bool drain(void* gdst, const void* ssrc, uint32_t byt
 }
 
 // Everything a warp emits for its 32 items besides the per-env scalars.  `sm` is the warp's staging block.
+//
+// Bulk-group protocol of lane 0 (groups complete in commit order): per group of 32 items the warp commits one
+// DENSE group (rewards + next_flat + non-spatial rows) and then one SPATIAL group per sub-tile.  A sub-tile store is
+// retired (waited for, its ones cleared) only right before the sub-tile buffer is needed again, so the last
+// spatial store of a group of items stays in flight while the warp computes the step of its next group.
 struct WarpEmitter {
   uint8_t* sm;
   const TileLayout* L;
   int lane;
-  bool pending;  // lane 0 has uncommitted/unwaited bulk stores reading this warp's staging block
+  bool dense_inflight;  // a DENSE group may still be reading the dense staging rows
+  bool sp_inflight;     // a SPATIAL group may still be reading the sub-tile buffer
+  bool dense_newer;     // the newest committed group is a DENSE one committed after the in-flight SPATIAL one
+  bool dirty;           // this lane has ones set in the sub-tile buffer at dirty_row (described by dirty_po)
+  float* dirty_row;
+  PlaneOffsets dirty_po;
 
+  __device__ __forceinline__ void init(uint8_t* block, const TileLayout* layout, int ln) {
+    sm = block; L = layout; lane = ln;
+    dense_inflight = sp_inflight = dense_newer = dirty = false;
+    dirty_row = nullptr;
+    dirty_po.w[0] = dirty_po.w[1] = dirty_po.w[2] = 0; dirty_po.n = 0;
+  }
   __device__ __forceinline__ float* sp() const { return reinterpret_cast<float*>(sm + L->sp_off); }
   __device__ __forceinline__ float* ns() const { return reinterpret_cast<float*>(sm + L->ns_off); }
   __device__ __forceinline__ uint8_t* rew() const { return sm + L->rew_off; }
   __device__ __forceinline__ float* nf() const { return reinterpret_cast<float*>(sm + L->nf_off); }
 
-  // the TMA engine must be done READING the staging block before the warp overwrites it
-  __device__ __forceinline__ void acquire() {
-    if (pending) {
-      if (lane == 0) bulk_wait_read_all();
-      pending = false;
+  // before the dense staging rows are overwritten: the previous DENSE group has been read by the TMA engine
+  __device__ __forceinline__ void acquire_dense() {
+    if (dense_inflight) {
+      if (lane == 0) {
+        if (sp_inflight && !dense_newer) bulk_wait_read_all_but_newest();  // the spatial group is newer: let it fly
+        else bulk_wait_read_all();
+      }
+      if (!(sp_inflight && !dense_newer)) sp_inflight = false;
+      dense_inflight = false;
+      dense_newer = false;
     }
     __syncwarp();
+  }
+  __device__ __forceinline__ void committed_dense() { dense_inflight = true; dense_newer = sp_inflight; }
+
+  // before the sub-tile buffer is reused: its previous store has been read, then the ones it carried are cleared
+  __device__ __forceinline__ void retire_spatial() {
+    if (sp_inflight) {
+      if (lane == 0) {
+        if (dense_newer) bulk_wait_read_all_but_newest();  // the DENSE group committed after it may keep flying
+        else bulk_wait_read_all();
+      }
+      if (!dense_newer) dense_inflight = false;
+      sp_inflight = false;
+    }
+    __syncwarp();
+    if (dirty) put_planes(dirty_po, dirty_row, 0.0f);
+    dirty = false;
   }
 
   __device__ __forceinline__ void zero_spatial() {  // once per kernel: the spatial sub-tile is zero between uses
@@ -88,19 +126,20 @@ struct WarpEmitter {
 
 // Feature encode of the warp's 32 items through the staging block (same outputs as warp_encode()).
 // Call with all 32 lanes; `cnt` items exist starting at item0; lane's item exists iff `have`.
+// `dense_open`: the caller already acquired the dense rows and issued (uncommitted) rewards / next_flat stores.
 __device__ __forceinline__ void warp_encode_tma(const DevConfig& c, const DevEncode& enc, const GridTables& tb,
                                                 WarpEmitter& em, const ObsState& o, int64_t item0, int cnt, bool have,
                                                 int64_t n_items, float* __restrict__ spatial,
-                                                float* __restrict__ non_spatial, bool ns_already_acquired) {
+                                                float* __restrict__ non_spatial, bool dense_open, bool dense_any) {
   const int lane = em.lane, A = c.A;
   const TileLayout& L = *em.L;
   const int F = enc.ns_floats, R = enc.sp_floats;
   // ---- dense rows: every lane writes its item's rows [view][lane][F]; one bulk store per view
-  if (!ns_already_acquired) em.acquire();
+  if (!dense_open) em.acquire_dense();
   float* ns = em.ns();
   if (have) {
     if (enc.kind == SUS_ENCODE_GLOBAL) {
-      for (int k = 0; k < A; ++k) global_ns_row(c, o, k, ns + (k * 32 + lane) * F);
+      global_ns_rows(c, o, ns + lane * F, 32 * F);
     } else if (enc.kind == SUS_ENCODE_PERSPECTIVE) {
       for (int k = 0; k < A; ++k) persp_ns_row(c, o, k, ns + (k * 32 + lane) * F);
     } else {
@@ -111,41 +150,37 @@ __device__ __forceinline__ void warp_encode_tma(const DevConfig& c, const DevEnc
   fence_proxy_async_smem();
   __syncwarp();
   const int views = enc.kind == SUS_ENCODE_FLAT ? 1 : A;
-  bool any = false;
+  bool any = dense_any;
   for (int k = 0; k < views; ++k)
     any |= drain(non_spatial + ((int64_t)k * n_items + item0) * F, ns + k * 32 * F, (uint32_t)(cnt * F * 4), lane);
   if (any) {
     if (lane == 0) bulk_commit();
-    em.pending = true;
+    em.committed_dense();
   }
   if (R == 0) return;
   // ---- sparse planes: G items at a time through the persistently-zero sub-tile
   const int G = L.G;
   const int sp_views = enc.kind == SUS_ENCODE_GLOBAL ? 1 : A;
   float* sp = em.sp();
-  for (int g0 = 0; g0 < cnt; g0 += G) {
-    const int gc = cnt - g0 < G ? cnt - g0 : G;
-    const bool mine = have && lane >= g0 && lane < g0 + G;
-    for (int k = 0; k < sp_views; ++k) {
-      if (mine) {
-        if (enc.kind == SUS_ENCODE_GLOBAL) scatter_planes(c, o, sp + (lane - g0) * R, [](int i) { return i; }, 1.0f);
-        else scatter_planes(c, o, sp + (lane - g0) * R, [k](int i) { return persp_channel_of_agent(k, i); }, 1.0f);
+  PlaneOffsets po = plane_offsets(c, o, [](int i) { return i; });  // Global planes (= view 0 of Perspective)
+  for (int k = 0; k < sp_views; ++k) {
+    if (k > 0) po = plane_offsets(c, o, [k](int i) { return persp_channel_of_agent(k, i); });
+    for (int g0 = 0; g0 < cnt; g0 += G) {
+      const int gc = cnt - g0 < G ? cnt - g0 : G;
+      em.retire_spatial();
+      if (have && lane >= g0 && lane < g0 + G) {
+        em.dirty = true; em.dirty_po = po; em.dirty_row = sp + (lane - g0) * R;
+        put_planes(po, em.dirty_row, 1.0f);
       }
       fence_proxy_async_smem();
       __syncwarp();
-      const bool b = drain(spatial + ((int64_t)k * n_items + item0 + g0) * R, sp, (uint32_t)(gc * R * 4), lane);
-      if (b) {
-        if (lane == 0) { bulk_commit(); bulk_wait_read_all(); }
-        em.pending = false;  // the wait covered every outstanding group of this lane
-      }
-      __syncwarp();
-      if (mine) {
-        if (enc.kind == SUS_ENCODE_GLOBAL) scatter_planes(c, o, sp + (lane - g0) * R, [](int i) { return i; }, 0.0f);
-        else scatter_planes(c, o, sp + (lane - g0) * R, [k](int i) { return persp_channel_of_agent(k, i); }, 0.0f);
+      if (drain(spatial + ((int64_t)k * n_items + item0 + g0) * R, sp, (uint32_t)(gc * R * 4), lane)) {
+        if (lane == 0) bulk_commit();
+        em.sp_inflight = true;
+        em.dense_newer = false;
       }
     }
   }
-  __syncwarp();
 }
 
 }  // namespace susnet
