@@ -307,34 +307,50 @@ def run_b200_arm(args):
         del rec
         env = make_env()
         env.reset()
-        h_rewards = torch.empty((N, A), dtype=torch.float32).pin_memory()
-        h_done = torch.empty(N, dtype=torch.bool).pin_memory()
-        h_trunc = torch.empty(N, dtype=torch.bool).pin_memory()
-        d_actions = torch.empty((N, A), dtype=torch.int32, device=dev)
-
-        def e2e_step(k):
-            d_actions.copy_(host_actions[k], non_blocking=True)           # H2D from pinned memory
-            _nf, r, d, t, _ = env.step(d_actions, featurizer=feat)       # fused step + encode
-            h_rewards.copy_(r, non_blocking=True)                         # D2H
-            h_done.copy_(d, non_blocking=True)
-            h_trunc.copy_(t, non_blocking=True)
-
+        torch.cuda.synchronize(dev)
+        stepper = S.HostStepper(env, featurizer=feat)   # public API: 3 streams x 2 slots, H2D | kernel | D2H overlap
         for k in range(W):
-            e2e_step(k)
+            stepper.step(host_actions[k])
+        stepper.drain()
         barrier()
         s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s4.record()
         for k in range(W, W + K):
-            e2e_step(k)
+            slot = stepper.step(host_actions[k])
+        stepper.drain()
         e4.record()
         barrier()
+        h_rewards, h_done, h_trunc = stepper.wait(slot)
         env.check_actions()  # every replayed action was valid for its agent's role
         e2e_ms = max_over_ranks(s4.elapsed_time(e4), device=dev)
+        # the same chain on ONE stream (no overlap between the copies and the kernel), for reference
+        seq = make_env()
+        seq.reset()
+        d_actions = torch.empty((N, A), dtype=torch.int32, device=dev)
+
+        def seq_step(k):
+            d_actions.copy_(host_actions[k], non_blocking=True)
+            _nf, r, d, t, _ = seq.step(d_actions, featurizer=feat)
+            h_rewards.copy_(r, non_blocking=True); h_done.copy_(d, non_blocking=True); h_trunc.copy_(t, non_blocking=True)
+
+        for k in range(W):
+            seq_step(k)
+        barrier()
+        s5, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s5.record()
+        for k in range(W, W + K):
+            seq_step(k)
+        e5.record()
+        barrier()
+        seq_ms = max_over_ranks(s5.elapsed_time(e5), device=dev)
         e2e = {"value": world * N * K / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": world * N * A * 4, "d2h_bytes_per_step": world * N * (A * 4 + 2),
-               "note": "actions int32 from pinned host memory; rewards f32 + done + truncated back to pinned host "
-                       "memory; feature tensors stay in HBM for the Q-network"}
-        del env
+               "h2d_bytes_per_step": world * stepper.h2d_bytes_per_step,
+               "d2h_bytes_per_step": world * stepper.d2h_bytes_per_step,
+               "single_stream_value": world * N * K / (seq_ms * 1e-3),
+               "note": "sus_net_b200.HostStepper: int32 actions H2D from pinned host memory, fused step+encode, rewards f32 "
+                       "+ done + truncated D2H to pinned host memory every step (3 streams, 2 slots); feature tensors stay "
+                       "in HBM for the Q-network"}
+        del env, seq
 
     # ---- the one collective of the path: final episode-statistics reduce (NCCL)
     stats = reduce_episode_stats(stats_local)

@@ -396,7 +396,7 @@ class BatchedFourRoomEnv:
         return self._actions[0].cpu().numpy().astype(int)
 
     # ------------------------------------------------------------------ step (base.py:332-407)
-    def step(self, agent_actions=None, featurizer=None, check=None):
+    def step(self, agent_actions=None, featurizer=None, check=None, out=None):
         """One env step for every env.
 
         agent_actions: (N, A) (batched) or (A,) (reference mode) role-list indices; None in batched mode means the
@@ -404,7 +404,9 @@ class BatchedFourRoomEnv:
         featurizer: optional sus_net_b200 featurizer; its tensors are written by the same kernel launch from the
         state the next action is taken from (batched mode, T = 1).
         check: validate action indices on the device and raise IndexError like the reference (synchronises);
-        defaults to True in reference mode, False in batched mode."""
+        defaults to True in reference mode, False in batched mode.
+        out: batched mode only -- `(rewards (N,A) f32|f64, dones (N,) bool, truncated (N,) bool)` device tensors to
+        write instead of the env's own output buffers (double-buffering by `HostStepper`)."""
         if not self._was_reset:
             raise AssertionError("reset() must be called before step()")
         N, A = self.num_envs, self.n_agents
@@ -428,10 +430,11 @@ class BatchedFourRoomEnv:
             assert tuple(keep.shape) == (N, A), f"Expected actions of shape {(N, A)}, got {tuple(keep.shape)}"
             io.actions = keep.data_ptr()
             io.actions_dtype = _TORCH_TO_SUS[keep.dtype]
-        io.rewards = self._rewards.data_ptr()
-        io.rewards_dtype = _TORCH_TO_SUS[self._rewards.dtype]
-        io.done = self._done.data_ptr()
-        io.truncated = self._trunc.data_ptr()
+        rewards, done, trunc = (self._rewards, self._done, self._trunc) if out is None else out
+        io.rewards = rewards.data_ptr()
+        io.rewards_dtype = _TORCH_TO_SUS[rewards.dtype]
+        io.done = done.data_ptr()
+        io.truncated = trunc.data_ptr()
         if self.emit_next_states:
             io.next_flat = self._next_flat.data_ptr()
         if self._metrics_buf is not None:
@@ -446,7 +449,7 @@ class BatchedFourRoomEnv:
         if check if check is not None else not self.batched:
             L.check(self.lib.sus_env_check_actions(self._h, self._stream()))
         if self.batched:
-            return (self._next_flat if self.emit_next_states else None), self._rewards, self._done, self._trunc, {}
+            return (self._next_flat if self.emit_next_states else None), rewards, done, trunc, {}
         self._sync_host()
         rewards = self._rewards[0].cpu().numpy().copy()
         return (self._full_state_tuple(), rewards, bool(self._done[0].item()), bool(self._trunc[0].item()),

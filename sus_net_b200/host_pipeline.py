@@ -1,0 +1,67 @@
+"""Host-buffer driver for a batched env: actions arrive in (pinned) host memory, rewards / dones / truncations go
+back to pinned host memory, and the three legs of a step -- H2D copy, fused step(+encode) kernel, D2H copy -- run on
+three CUDA streams over two rotating slots, so consecutive steps overlap (PCIe is full duplex).  The feature tensors
+stay on the device for the consumer (the Q-network).  No reference analogue: the reference is a host-only loop."""
+import torch
+
+
+class HostStepper:
+    def __init__(self, env, featurizer=None, slots=2):
+        assert env.batched, "HostStepper drives batched envs"
+        self.env, self.featurizer, self.slots = env, featurizer, slots
+        dev, N, A = env.device, env.num_envs, env.n_agents
+        self.s_h2d, self.s_run, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
+        self.d_actions = [torch.empty((N, A), dtype=torch.int32, device=dev) for _ in range(slots)]
+        self.d_out = [(torch.empty((N, A), dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.bool, device=dev),
+                       torch.empty(N, dtype=torch.bool, device=dev)) for _ in range(slots)]
+        self.h_out = [(torch.empty((N, A), dtype=torch.float32).pin_memory(), torch.empty(N, dtype=torch.bool).pin_memory(),
+                       torch.empty(N, dtype=torch.bool).pin_memory()) for _ in range(slots)]
+        self.ev_h2d = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_run = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_d2h = [torch.cuda.Event() for _ in range(slots)]
+        self.k = 0
+        start = torch.cuda.current_stream(dev)
+        for s in (self.s_h2d, self.s_run, self.s_d2h):
+            s.wait_stream(start)
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.d_actions[0].numel() * 4
+
+    @property
+    def d2h_bytes_per_step(self):
+        return sum(t.numel() * t.element_size() for t in self.d_out[0])
+
+    def step(self, host_actions):
+        """Enqueue one step on `host_actions` ((N, A) int32, ideally pinned).  Returns the slot whose pinned host
+        buffers `(rewards, dones, truncated)` will hold the results once `wait(slot)` returns."""
+        slot = self.k % self.slots
+        first_use = self.k < self.slots
+        with torch.cuda.stream(self.s_h2d):
+            if not first_use:
+                self.s_h2d.wait_event(self.ev_run[slot])  # the kernel that read this action buffer has finished
+            self.d_actions[slot].copy_(host_actions, non_blocking=True)
+            self.ev_h2d[slot].record(self.s_h2d)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(self.ev_h2d[slot])
+            if not first_use:
+                self.s_run.wait_event(self.ev_d2h[slot])  # the previous results of this slot have left the device
+            self.env.step(self.d_actions[slot], featurizer=self.featurizer, out=self.d_out[slot])
+            self.ev_run[slot].record(self.s_run)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.ev_run[slot])
+            for h, d in zip(self.h_out[slot], self.d_out[slot]):
+                h.copy_(d, non_blocking=True)
+            self.ev_d2h[slot].record(self.s_d2h)
+        self.k += 1
+        return slot
+
+    def wait(self, slot):
+        self.ev_d2h[slot].synchronize()
+        return self.h_out[slot]
+
+    def drain(self):
+        """Make the current stream wait for everything enqueued so far."""
+        cur = torch.cuda.current_stream(self.env.device)
+        for s in (self.s_h2d, self.s_run, self.s_d2h):
+            cur.wait_stream(s)
