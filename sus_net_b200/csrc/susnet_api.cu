@@ -139,20 +139,60 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ Rese
   store_state(p.st, e, s, true);
 }
 
+// ---- everything a step reads for one env, as raw words: loaded one group ahead by the TMA kernel so the DRAM
+// latency of the state records and the action rows hides behind the previous group's work
+struct StepInput {
+  uint64_t pos, jobpos;
+  uint4 aux, met;
+  uint64_t acts;  // one byte per agent
+  uint32_t oob;   // an action was negative or >= 256
+};
+
+__device__ __forceinline__ void load_input(const StepParams& p, int64_t e, bool have, StepInput& in) {
+  in.pos = in.jobpos = in.acts = 0; in.oob = 0;
+  in.aux = in.met = make_uint4(0, 0, 0, 0);
+  if (!have) return;
+  const int A = p.c.A;
+  in.pos = p.st.pos[e]; in.jobpos = p.st.jobpos[e]; in.aux = p.st.aux[e]; in.met = p.st.met[e];
+  if (p.actions == nullptr) return;
+  if (p.actions_dtype == SUS_I32) {
+    const int32_t* a = static_cast<const int32_t*>(p.actions) + e * A;
+    for (int i = 0; i < A; ++i) { const uint32_t v = (uint32_t)a[i]; in.oob |= v & ~0xffu; in.acts |= (uint64_t)(v & 0xffu) << (8 * i); }
+  } else if (p.actions_dtype == SUS_I64) {
+    const long long* a = static_cast<const long long*>(p.actions) + e * A;
+    for (int i = 0; i < A; ++i) {
+      const unsigned long long v = (unsigned long long)a[i];
+      in.oob |= (v & ~0xffull) ? 1u << 8 : 0u;
+      in.acts |= (uint64_t)(v & 0xffull) << (8 * i);
+    }
+  } else {
+    const uint8_t* a = static_cast<const uint8_t*>(p.actions) + e * A;
+    for (int i = 0; i < A; ++i) in.acts |= (uint64_t)a[i] << (8 * i);
+  }
+}
+
+__device__ __forceinline__ void unpack_state(const StepInput& in, EnvState& s) {
+  s.pos = in.pos; s.jobpos = in.jobpos;
+  s.alive = in.aux.x & 0xff; s.imp = (in.aux.x >> 8) & 0xff; s.jobdone = (in.aux.x >> 16) & 0xff; s.used = in.aux.x >> 24;
+  s.nsteps = in.aux.y; s.timer = in.aux.z; s.tagcnt = in.aux.w;
+  s.completed = in.met.x; s.sabotaged = in.met.y; s.misc = in.met.z;
+}
+
 // ---- the step of one env, shared by the direct-store kernel (k_step) and the TMA-staged kernel (k_step_tma).
 // rew_row / nf_row point at THIS env's reward / next_flat row: in global memory (direct) or in the warp's
 // shared-memory staging block (TMA path).
 template <int VARIANT>
-__device__ __forceinline__ void step_one(const StepParams& p, const GridTables& tb, int64_t e, bool have, void* rew_row,
-                                         float* nf_row, EnvState& s, StepResult& r, bool& stepped, bool& finished) {
+__device__ __forceinline__ void step_one(const StepParams& p, const GridTables& tb, int64_t e, bool have,
+                                         const StepInput& in, void* rew_row, float* nf_row, EnvState& s, StepResult& r,
+                                         bool& stepped, bool& finished) {
   const DevConfig& c = p.c;
   const int A = c.A;
   stepped = false;
   finished = false;
   if (!have) return;
-  load_state(p.st, e, s);
+  unpack_state(in, s);
   // ---- actions: role-list indices, one byte per agent
-  uint64_t acts = 0;
+  uint64_t acts = in.acts;
   bool ok = true;
   if (p.actions == nullptr) {  // fused random policy == env.step(env.sample_actions()), base.py:326-330
     WordStream wa;
@@ -160,14 +200,10 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
     for (int i = 0; i < A; ++i)
       acts |= (uint64_t)bounded(wa.word(i), n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) << (8 * i);
   } else {
-    for (int i = 0; i < A; ++i) {
-      long long a;
-      if (p.actions_dtype == SUS_I32) a = static_cast<const int32_t*>(p.actions)[e * A + i];
-      else if (p.actions_dtype == SUS_I64) a = static_cast<const long long*>(p.actions)[e * A + i];
-      else a = static_cast<const uint8_t*>(p.actions)[e * A + i];
-      if (a < 0 || a >= (long long)n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) { ok = false; a = 0; }
-      acts |= (uint64_t)a << (8 * i);
-    }
+    ok = in.oob == 0;
+    for (int i = 0; i < A; ++i)
+      if (get_byte(acts, i) >= n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) ok = false;
+    if (!ok) acts = 0;
   }
   if (p.actions_out)
     for (int i = 0; i < A; ++i) p.actions_out[e * A + i] = (int32_t)get_byte(acts, i);
@@ -245,7 +281,9 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepP
   bool stepped, finished;
   EnvState s = {};
   StepResult r = {};
-  step_one<VARIANT>(p, tb, e, have,
+  StepInput in;
+  load_input(p, e, have, in);
+  step_one<VARIANT>(p, tb, e, have, in,
                     p.rewards ? static_cast<uint8_t*>(p.rewards) + e * p.c.A * (p.rewards_dtype == SUS_F64 ? 8 : 4) : nullptr,
                     p.next_flat ? p.next_flat + e * p.c.S : nullptr, s, r, stepped, finished);
   finish_one(p, tb, e, lane, s, r, stepped, finished);
@@ -270,16 +308,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_step_tma(const __grid_constant_
   if (ENCODE && p.enc.sp_floats > 0) em.zero_spatial();
   const int64_t n_groups = (p.N + 31) >> 5;
   const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
-  for (int64_t g = (int64_t)blockIdx.x * L.warps + warp; g < n_groups; g += (int64_t)gridDim.x * L.warps) {
+  const int64_t g_stride = (int64_t)gridDim.x * L.warps;
+  if (L.stagger_ns > 0 && warp > 0) __nanosleep((unsigned)(warp * L.stagger_ns));
+  StepInput in, in_next;
+  {
+    const int64_t g = (int64_t)blockIdx.x * L.warps + warp;
+    load_input(p, (g << 5) + lane, g < n_groups && (g << 5) + lane < p.N, in);
+  }
+  for (int64_t g = (int64_t)blockIdx.x * L.warps + warp; g < n_groups; g += g_stride) {
     const int64_t e0 = g << 5, e = e0 + lane;
     const bool have = e < p.N;
+    {  // prefetch the next group's state records and action rows
+      const int64_t gn = g + g_stride, en = (gn << 5) + lane;
+      load_input(p, en, gn < n_groups && en < p.N, in_next);
+    }
     const int64_t rem = p.N - e0;
     const int cnt = rem < 32 ? (int)rem : 32;
     bool stepped, finished;
     EnvState s = {};
     StepResult r = {};
     em.acquire_dense();  // the previous group's dense bulk stores have finished reading the staging rows
-    step_one<VARIANT>(p, tb, e, have, p.rewards ? em.rew() + lane * A * rew_elem : nullptr,
+    step_one<VARIANT>(p, tb, e, have, in, p.rewards ? em.rew() + lane * A * rew_elem : nullptr,
                       p.next_flat ? em.nf() + lane * p.c.S : nullptr, s, r, stepped, finished);
     finish_one(p, tb, e, lane, s, r, stepped, finished);
     // an env whose actions were rejected keeps its old outputs: do not publish the stale staging rows
@@ -309,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step_tma(const __grid_constant_
     }
     if (ENCODE)
       warp_encode_tma(p.c, p.enc, tb, em, obs_of(s), e0, cnt, have, p.N, p.spatial, p.non_spatial, true, dense_any);
+    in = in_next;
   }
   em.finish();
 }
@@ -620,6 +670,8 @@ bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool wa
     if (best.warps == kThreads / 32) break;
   }
   if (best.warps < 2) return false;
+  const char* env_s = std::getenv("SUSNET_STAGGER_NS");
+  best.stagger_ns = env_s ? std::atoi(env_s) : 0;
   L = best;
   return true;
 }

@@ -87,8 +87,12 @@ __device__ __forceinline__ PlaneOffsets plane_offsets(const DevConfig& c, const 
 }
 
 __device__ __forceinline__ void put_planes(const PlaneOffsets& po, float* __restrict__ row, float v) {
-  for (int q = 0; q < po.n; ++q) {
-    const uint32_t off = po.get(q);
+  uint64_t x = po.w[0];
+  for (int q = 0; q < po.n; ++q) {  // walk the 10-bit fields by shifting (no dynamic field index)
+    if (q == 6) x = po.w[1];
+    if (q == 12) x = po.w[2];
+    const uint32_t off = (uint32_t)x & 0x3ffu;
+    x >>= 10;
     if (off != 0x3ffu) row[off] = v;
   }
 }
@@ -123,22 +127,25 @@ __device__ __forceinline__ void persp_ns_row(const DevConfig& c, const ObsState&
 // same in every Global view, so each value is converted once and stored A times.
 __device__ __forceinline__ void global_ns_rows(const DevConfig& c, const ObsState& o, float* __restrict__ base, int stride) {
   const int A = c.A, J = c.J;
-  int p = 0;
-  for (int i = 0; i < A; ++i, ++p) {
+  float* col = base;  // column p of view 0; view k is k * stride further
+  for (int i = 0; i < A; ++i, ++col) {
     const float v = (float)((o.alive >> i) & 1u);
-    for (int k = 0; k < A; ++k) base[k * stride + p] = v;
+    float* w = col;
+    for (int k = 0; k < A; ++k, w += stride) *w = v;
   }
   if (c.variant == SUS_VARIANT_TAGGING)
-    for (int i = 0; i < A; ++i, ++p) {
+    for (int i = 0; i < A; ++i, ++col) {
       const float v = (float)((o.tagcnt >> (4 * i)) & 15u);
-      for (int k = 0; k < A; ++k) base[k * stride + p] = v;
+      float* w = col;
+      for (int k = 0; k < A; ++k, w += stride) *w = v;
     }
-  for (int j = 0; j < J; ++j, ++p) {
+  for (int j = 0; j < J; ++j, ++col) {
     const float v = (float)((o.jobdone >> j) & 1u);
-    for (int k = 0; k < A; ++k) base[k * stride + p] = v;
+    float* w = col;
+    for (int k = 0; k < A; ++k, w += stride) *w = v;
   }
-  for (int k = 0; k < A; ++k)
-    for (int i = 0; i < A; ++i) base[k * stride + p + i] = i == k ? 1.0f : 0.0f;
+  for (int k = 0; k < A; ++k, col += stride)  // one-hot of the view index
+    for (int i = 0; i < A; ++i) col[i] = i == k ? 1.0f : 0.0f;
 }
 
 __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }

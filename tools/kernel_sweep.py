@@ -61,6 +61,11 @@ def main():
         med, best = time_fused(N, a.steps)
         out[f"G{g}_W{w}"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
     os.environ.pop("SUSNET_TILE_G"); os.environ.pop("SUSNET_TILE_WARPS")
+    for st in (500, 1000, 1500, 2000, 2500, 3000, 4000):
+        os.environ["SUSNET_STAGGER_NS"] = str(st)
+        med, best = time_fused(N, a.steps)
+        out[f"stagger_{st}"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
+    os.environ.pop("SUSNET_STAGGER_NS")
     med, best = time_fused(N, a.steps, policy_fused=True)
     out["default_fused_policy"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
     for n in (1 << 16, 1 << 18, 1 << 22):
