@@ -146,6 +146,8 @@ typedef struct SusStepIO {
   float *next_flat;        /* [N][S] post-step, PRE-reset state in flatten order = the row the reference
                               stores in next_states[:, -1] (train.py:388-399, replay_memory.py:120-126) */
   int64_t *metrics;        /* [N][SUS_N_METRICS] pre-reset episode counters = the step's `info` dict */
+  int16_t *imposters;      /* [N][n_imposters] ascending agent ids of the imposters of the episode the step belonged
+                              to (pre-reset env.imposter_idxs: the `imposters` replay column, replay_memory.py:42-44) */
   const SusEncodeSpec *encode; /* host pointer or NULL: fused encode of the state the NEXT action is
                               taken from (post auto-reset), written to spatial / non_spatial below */
   float *spatial;          /* [views_s][N][spatial_floats]  */
@@ -223,6 +225,37 @@ int sus_env_state_arrays(sus_env_t env, void **ptrs /*host [4]*/, int32_t *bytes
  * stream (step_words [N][2A-1], reset_words [N][n_imp+A+J], act_words [N][A]); NULL leaves a stream alone. */
 int sus_env_debug_inject_words(sus_env_t env, const uint32_t *step_words, const uint32_t *reset_words,
                                const uint32_t *act_words);
+
+/* ---- row (f1): replay ring in the reference layout (src/replay_memory.py:33-44) -------------------------
+ * One launch stores the N transitions of a batched step at ring slots (idx + e) mod M and advances every env's
+ * T-deep state sequence exactly like ReplayBuffer.populate / train() do on the host: next_sequence =
+ * np.roll(sequence, -1, axis=0) with the new state in the last row (replay_memory.py:120-126, train.py:388-389);
+ * an env whose episode ended restarts from T copies of its reset state (replay_memory.py:107-112,
+ * train.py:440-445). */
+typedef struct SusReplayPush {
+  int64_t N, M, idx;          /* transitions per launch, ring capacity, first slot */
+  int32_t T, S, A, n_imposters;
+  const float *seq_in;        /* [N][T][S] running state sequence of every env before the step */
+  float *seq_out;             /* [N][T][S] the sequence the next step starts from (must not alias seq_in) */
+  const float *next_flat;     /* [N][S] post-step, pre-reset state (SusStepIO.next_flat) */
+  const float *cur_flat;      /* [N][S] state the next action is taken from (sus_env_export_flat) */
+  const void *actions;        /* [N][A] */
+  int32_t actions_dtype;      /* SUS_U8 / SUS_I32 / SUS_I64 */
+  int32_t reserved;
+  const float *rewards;       /* [N][A] */
+  const uint8_t *done;        /* [N] */
+  const uint8_t *truncated;   /* [N] */
+  const int16_t *imposters;   /* [N][n_imposters] (SusStepIO.imposters) */
+  float *states;              /* [M][T][S]  ReplayBuffer.states      */
+  int64_t *r_actions;         /* [M][A]     ReplayBuffer.actions     */
+  float *r_rewards;           /* [M][A]     ReplayBuffer.rewards     */
+  float *next_states;         /* [M][T][S]  ReplayBuffer.next_states */
+  uint8_t *r_dones;           /* [M][1]     ReplayBuffer.dones       */
+  int16_t *r_imposters;       /* [M][n_imp] ReplayBuffer.imposters   */
+} SusReplayPush;
+
+/* ReplayBuffer.add (replay_memory.py:50-72) for a whole batched step; the caller advances idx/size. */
+int sus_replay_push(const SusReplayPush *args /*host*/, int device, void *stream);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t sus_launch_count(void);

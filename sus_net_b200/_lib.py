@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "sus_env_sample_actions", "sus_env_export_flat", "sus_env_import_flat", "sus_env_export_imposter_mask",
     "sus_env_export_metrics", "sus_env_encode", "sus_encode_from_flat", "sus_env_stats", "sus_env_clear_stats",
     "sus_env_get_ticks", "sus_env_set_ticks", "sus_env_state_arrays", "sus_env_debug_inject_words",
-    "sus_launch_count",
+    "sus_launch_count", "sus_replay_push",
 )
 
 
@@ -48,8 +48,20 @@ class SusStepIO(C.Structure):
     _fields_ = [
         ("actions", C.c_void_p), ("actions_dtype", C.c_int32), ("rewards_dtype", C.c_int32), ("rewards", C.c_void_p),
         ("done", C.c_void_p), ("truncated", C.c_void_p), ("actions_out", C.c_void_p), ("next_flat", C.c_void_p),
-        ("metrics", C.c_void_p), ("encode", C.POINTER(SusEncodeSpec)), ("spatial", C.c_void_p),
+        ("metrics", C.c_void_p), ("imposters", C.c_void_p), ("encode", C.POINTER(SusEncodeSpec)), ("spatial", C.c_void_p),
         ("non_spatial", C.c_void_p),
+    ]
+
+
+class SusReplayPush(C.Structure):
+    _fields_ = [
+        ("N", C.c_int64), ("M", C.c_int64), ("idx", C.c_int64),
+        ("T", C.c_int32), ("S", C.c_int32), ("A", C.c_int32), ("n_imposters", C.c_int32),
+        ("seq_in", C.c_void_p), ("seq_out", C.c_void_p), ("next_flat", C.c_void_p), ("cur_flat", C.c_void_p),
+        ("actions", C.c_void_p), ("actions_dtype", C.c_int32), ("reserved", C.c_int32),
+        ("rewards", C.c_void_p), ("done", C.c_void_p), ("truncated", C.c_void_p), ("imposters", C.c_void_p),
+        ("states", C.c_void_p), ("r_actions", C.c_void_p), ("r_rewards", C.c_void_p), ("next_states", C.c_void_p),
+        ("r_dones", C.c_void_p), ("r_imposters", C.c_void_p),
     ]
 
 
@@ -97,6 +109,7 @@ def lib():
         "sus_env_state_arrays": ([vp, C.POINTER(vp), C.POINTER(i32)], C.c_int),
         "sus_env_debug_inject_words": ([vp, vp, vp, vp], C.c_int),
         "sus_launch_count": ([], i64),
+        "sus_replay_push": ([C.POINTER(SusReplayPush), C.c_int, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)

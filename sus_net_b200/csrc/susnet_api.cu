@@ -63,6 +63,7 @@ struct StepParams {
   int32_t* actions_out;
   float* next_flat;
   long long* metrics;
+  int16_t* imposters;
   float* spatial;
   float* non_spatial;
   const uint32_t* inj_step;
@@ -228,6 +229,11 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
   if (p.done) p.done[e] = r.done;
   if (p.trunc) p.trunc[e] = r.trunc;
   if (nf_row) write_flat<float>(c, s, nf_row);
+  if (p.imposters) {  // ascending ids = env.imposter_idxs of this episode (before any auto-reset)
+    int k = 0;
+    for (int i = 0; i < A; ++i)
+      if ((s.imp >> i) & 1u) p.imposters[e * c.nI + k++] = (int16_t)i;
+  }
   if (p.metrics) {
     long long* m = p.metrics + e * SUS_N_METRICS;
     m[SUS_M_TOTAL_TIME_STEPS] = s.nsteps; m[SUS_M_IMP_KILLED_CREW] = s.misc & 0xff;
@@ -713,6 +719,10 @@ struct SusEnv {
 
 extern "C" {
 
+// shared with the other translation units of the library (not part of the public ABI)
+int sus_internal_fail(int code, const char* msg) { return fail(code, msg); }
+void sus_internal_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int sus_abi_version(void) { return SUS_ABI_VERSION; }
 const char* sus_last_error(void) { return g_last_error.c_str(); }
 int64_t sus_launch_count(void) { return g_launches.load(); }
@@ -811,7 +821,7 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   p.st = e->st;
   p.actions = io->actions; p.actions_dtype = io->actions_dtype; p.rewards = io->rewards; p.rewards_dtype = io->rewards_dtype;
   p.done = io->done; p.trunc = io->truncated; p.actions_out = io->actions_out; p.next_flat = io->next_flat;
-  p.metrics = reinterpret_cast<long long*>(io->metrics); p.spatial = io->spatial; p.non_spatial = io->non_spatial;
+  p.metrics = reinterpret_cast<long long*>(io->metrics); p.imposters = io->imposters; p.spatial = io->spatial; p.non_spatial = io->non_spatial;
   p.inj_step = e->inj_step; p.inj_reset = e->inj_reset; p.inj_act = e->inj_act;
   p.stats = e->stats; p.err = e->err; p.tick = e->step_tick++; p.N = e->N;
   e->inj_step = e->inj_reset = e->inj_act = nullptr;

@@ -161,6 +161,9 @@ class BatchedFourRoomEnv:
         self._next_flat = torch.zeros((N, S), dtype=torch.float32, device=dev)
         self._metrics_buf = torch.zeros((N, L.N_METRICS), dtype=torch.int64, device=dev) if not self.batched else None
         self.emit_next_states = True  # batched mode: write the (N, S) replay-layout next-state rows every step
+        self.emit_imposters = False   # batched mode: also write the (N, n_imposters) int16 replay column
+        self._imposters_buf = None
+        self._last_actions = None     # (N, A) int32: the actions the last fused-random-policy step applied
         self._host_state = None  # reference mode: numpy mirror of the single env
         self._imp_cache = None
         self._was_reset = False
@@ -416,6 +419,10 @@ class BatchedFourRoomEnv:
             if not self.batched:
                 raise AssertionError(f"Expected {A} actions, got none")
             io.actions = None
+            if self.emit_imposters:  # a replay ring is attached: it needs the actions the random policy drew
+                if self._last_actions is None:
+                    self._last_actions = torch.zeros((N, A), dtype=torch.int32, device=self.device)
+                io.actions_out = self._last_actions.data_ptr()
         else:
             if not self.batched:
                 assert len(agent_actions) == A, f"Expected {A} actions, got {len(agent_actions)}"  # base.py:357-359
@@ -439,6 +446,10 @@ class BatchedFourRoomEnv:
             io.next_flat = self._next_flat.data_ptr()
         if self._metrics_buf is not None:
             io.metrics = self._metrics_buf.data_ptr()
+        if self.emit_imposters:
+            if self._imposters_buf is None:
+                self._imposters_buf = torch.zeros((N, self.n_imposters), dtype=torch.int16, device=self.device)
+            io.imposters = self._imposters_buf.data_ptr()
         spec = None
         if featurizer is not None:
             spec = featurizer._bind_for_fused_step(self)

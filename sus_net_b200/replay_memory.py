@@ -1,0 +1,152 @@
+"""GPU replay ring in the reference's layout (src/replay_memory.py) -- SURVEY.md row (f1).
+
+`ReplayBuffer` keeps the reference's constructor, tensor names, shapes and dtypes (`states (M,T,S) f32`, `actions
+(M,A) i64`, `rewards (M,A) f32`, `next_states (M,T,S) f32`, `dones (M,1) bool`, `imposters (M,n_imp) i16`), its
+`add` / `sample` / `populate` methods and the `Batch` namedtuple, so `DQNTeamTrainer.train_step` (train.py:50-149)
+consumes its batches unchanged -- but the tensors live on the env's device and a whole batched step (N transitions,
+including the T-deep `np.roll` sequence bookkeeping of replay_memory.py:107-134 / train.py:388-399,440-445) is stored
+by ONE kernel launch (`sus_replay_push`).
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .env import _TORCH_TO_SUS
+
+Batch = namedtuple("Batch", ("states", "actions", "rewards", "next_states", "imposters", "dones"))  # replay_memory.py:6-8
+
+
+class ReplayBuffer:
+    def __init__(self, max_size, state_size, trajectory_size, n_agents, n_imposters, device="cuda"):
+        assert max_size > 0, "Replay buffer size must be positive"  # replay_memory.py:21-24
+        assert trajectory_size > 0, "Trajectory size must be positive"
+        assert state_size > 0, "State size must be positive"
+        assert n_agents > 0, "Number of agents must be positive"
+        self.max_size, self.trajectory_size, self.state_size = max_size, trajectory_size, state_size
+        self.n_agents, self.n_imposters = n_agents, n_imposters
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        M, T, S, A, dev = max_size, trajectory_size, state_size, n_agents, self.device
+        self.states = torch.empty((M, T, S), device=dev)  # replay_memory.py:33-44
+        self.actions = torch.empty((M, A), dtype=torch.long, device=dev)
+        self.rewards = torch.empty((M, A), device=dev)
+        self.next_states = torch.empty((M, T, S), device=dev)
+        self.dones = torch.empty((M, 1), dtype=torch.bool, device=dev)
+        self.imposters = torch.empty((M, n_imposters), dtype=torch.int16, device=dev)
+        self.idx = 0
+        self.size = 0
+        self._env = None
+        self._seq = None
+
+    # ---------------------------------------------------------------- reference API
+    def add(self, state, action, reward, next_state, done, imposters):
+        """One transition (replay_memory.py:50-72)."""
+        i, dev = self.idx, self.device
+        self.states[i] = torch.as_tensor(np.asarray(state), dtype=torch.float32).to(dev)
+        self.actions[i] = torch.as_tensor(np.asarray(action)).to(dev)
+        self.rewards[i] = torch.as_tensor(np.asarray(reward), dtype=torch.float32).to(dev)
+        self.next_states[i] = torch.as_tensor(np.asarray(next_state), dtype=torch.float32).to(dev)
+        self.dones[i] = bool(done)
+        self.imposters[i] = torch.as_tensor(np.asarray(imposters)).to(dev)
+        self.idx = (self.idx + 1) % self.max_size
+        self.size = min(self.size + 1, self.max_size)
+
+    def sample(self, batch_size, generator=None):
+        """replay_memory.py:74-94: uniform with replacement over the filled part."""
+        assert self.size > 0, "Replay buffer is empty, can't sample"
+        sample_idx = torch.randint(0, self.size, (batch_size,), device=self.device, generator=generator)
+        return Batch(states=self.states[sample_idx], actions=self.actions[sample_idx], rewards=self.rewards[sample_idx],
+                     imposters=self.imposters[sample_idx], next_states=self.next_states[sample_idx],
+                     dones=self.dones[sample_idx])
+
+    def populate(self, env, num_steps):
+        """Fill with (at least) `num_steps` random-policy transitions (replay_memory.py:96-143).  With a batched env
+        every launch adds `env.num_envs` transitions; a reference-mode env is driven one step at a time exactly
+        like the reference does."""
+        if not env.batched:
+            return self._populate_single(env, num_steps)
+        self.attach(env)
+        launches = -(-int(num_steps) // env.num_envs)
+        for _ in range(launches):
+            self.collect_step(None)
+        return launches * env.num_envs
+
+    def _populate_single(self, env, num_steps):
+        step = 0
+        while step < num_steps:  # replay_memory.py:103-143
+            state_sequence = np.zeros((self.trajectory_size, self.state_size))
+            s, _ = env.reset()
+            state = env.flatten_state(s)
+            state_sequence[:] = state
+            done = truncation = False
+            while not done and not truncation:
+                imposters = env.imposter_idxs
+                action = env.sample_actions()
+                n_s, reward, done, truncation, _ = env.step(action)
+                next_state = env.flatten_state(n_s)
+                next_sequence = np.roll(state_sequence.copy(), -1, axis=0)
+                next_sequence[-1] = next_state.copy()
+                self.add(state_sequence, action, reward, next_sequence, done, imposters)
+                state_sequence = next_sequence
+                step += 1
+                if done or step >= num_steps:
+                    break
+        return step
+
+    # ---------------------------------------------------------------- batched collection
+    def attach(self, env):
+        """Bind a batched env (already reset, or reset here) and start every env's sequence from T copies of its
+        current state (replay_memory.py:107-112, train.py:318-322)."""
+        assert env.batched and env.device == self.device
+        assert env.flattened_state_size == self.state_size and env.n_agents == self.n_agents
+        assert env.num_envs <= self.max_size, "the ring must hold at least one batched step"
+        if not env._was_reset:
+            env.reset()
+        env.emit_next_states = True
+        env.emit_imposters = True
+        self._env = env
+        cur = env.flat_states()
+        seq = cur[:, None, :].expand(-1, self.trajectory_size, -1).contiguous()
+        self._seq = [seq, torch.empty_like(seq)]
+        self._cur_flat = cur
+
+    @property
+    def state_sequence(self):
+        """(N, T, S) f32: the sequence the next action of every env is taken from (train.py:346-348 featurizes it)."""
+        return self._seq[0]
+
+    def collect_step(self, actions=None, featurizer=None):
+        """env.step(actions) + ReplayBuffer.add for all N envs (one step launch, one export, one push launch).
+        Returns env.step's tuple."""
+        env = self._env
+        out = env.step(actions, featurizer=featurizer)
+        next_flat, rewards, dones, truncated, _ = out
+        applied = env._last_actions if actions is None else out_actions(actions, env)
+        env.flat_states(out=self._cur_flat)
+        N = env.num_envs
+        p = L.SusReplayPush(
+            N=N, M=self.max_size, idx=self.idx, T=self.trajectory_size, S=self.state_size, A=self.n_agents,
+            n_imposters=self.n_imposters, seq_in=self._seq[0].data_ptr(), seq_out=self._seq[1].data_ptr(),
+            next_flat=next_flat.data_ptr(), cur_flat=self._cur_flat.data_ptr(), actions=applied.data_ptr(),
+            actions_dtype=_TORCH_TO_SUS[applied.dtype], rewards=rewards.data_ptr(), done=dones.data_ptr(),
+            truncated=truncated.data_ptr(), imposters=env._imposters_buf.data_ptr(), states=self.states.data_ptr(),
+            r_actions=self.actions.data_ptr(), r_rewards=self.rewards.data_ptr(), next_states=self.next_states.data_ptr(),
+            r_dones=self.dones.data_ptr(), r_imposters=self.imposters.data_ptr())
+        L.check(env.lib.sus_replay_push(C.byref(p), self.device.index, env._stream()))
+        self._seq.reverse()
+        self.idx = (self.idx + N) % self.max_size
+        self.size = min(self.size + N, self.max_size)
+        return out
+
+
+def out_actions(actions, env):
+    """The (N, A) device tensor the step consumed (int32 / int64 / uint8, contiguous)."""
+    if isinstance(actions, torch.Tensor) and actions.device == env.device and actions.is_contiguous() and \
+            actions.dtype in (torch.uint8, torch.int32, torch.int64):
+        return actions
+    return torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions).to(
+        device=env.device, dtype=torch.int32).contiguous()

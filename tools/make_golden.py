@@ -102,6 +102,11 @@ def features(name, env, flat):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    replay_fixture("cfg4_base_1v4", T=1, M=100)
+    replay_fixture("base_2v3_j3", T=3, M=64)
+    replay_fixture("tagging_2v5_short", T=2, M=50)
+    if "--replay-only" in sys.argv:
+        return
     for name in CASES:
         for injected in (False, True):
             tr, env = trajectory(name, injected)
@@ -117,6 +122,52 @@ def main():
                     fpath = os.path.join(OUT, f"{name}.features.npz")
                     np.savez_compressed(fpath, **ft)
                     print(f"{fpath}: {os.path.getsize(fpath) / 1024:.1f} KiB, {flat.shape[0]} states")
+
+
+
+
+def replay_fixture(name, T, M, n_envs=6, n_steps=45):
+    """The reference's own ReplayBuffer (src/replay_memory.py) fed the way populate()/train() feed it, N envs in lock
+    step (ring order: step-major, env-minor).  Pins the layout, dtypes and the T-deep np.roll sequence bookkeeping."""
+    import torch
+
+    H.import_reference()
+    from src.replay_memory import ReplayBuffer as RefReplay
+
+    cfg = CASES[name]
+    ref = H.ReferenceBatch(cfg, n_envs, SEED, env_id_base=ENV_ID_BASE)
+    flat = ref.reset()
+    S = flat.shape[1]
+    buf = RefReplay(max_size=M, state_size=S, trajectory_size=T, n_agents=ref.A, n_imposters=ref.cfg["n_imposters"])
+    for t_ in (buf.states, buf.next_states, buf.rewards):
+        t_.zero_()
+    buf.actions.zero_(); buf.dones.zero_(); buf.imposters.zero_()
+    seqs = [np.repeat(flat[i][None].astype(np.float64), T, axis=0) for i in range(n_envs)]  # replay_memory.py:107-112
+    actions = []
+    for t in range(n_steps):
+        imps = [np.asarray(e.imposter_idxs).copy() for e in ref.envs]
+        a = ref.sample_actions()
+        o = ref.step(a)
+        cur = ref.flat_states()
+        actions.append(a)
+        for i in range(n_envs):
+            nxt = np.roll(seqs[i].copy(), -1, axis=0)  # replay_memory.py:121-126
+            nxt[-1] = o["next_flat"][i]
+            buf.add(state=seqs[i], action=a[i], reward=o["rewards"][i], next_state=nxt, done=bool(o["done"][i]),
+                    imposters=imps[i])
+            if o["done"][i] or o["trunc"][i]:
+                seqs[i] = np.repeat(cur[i][None].astype(np.float64), T, axis=0)  # train.py:440-445
+            else:
+                seqs[i] = nxt
+    out = dict(case=name, T=T, M=M, n_envs=n_envs, seed=SEED, env_id_base=ENV_ID_BASE,
+               actions=np.array(actions, dtype=np.int8), states=buf.states.numpy(), r_actions=buf.actions.numpy(),
+               rewards=buf.rewards.numpy(), next_states=buf.next_states.numpy(), dones=buf.dones.numpy(),
+               imposters=buf.imposters.numpy(), idx=buf.idx, size=buf.size,
+               final_seq=np.stack(seqs).astype(np.float32))
+    path = os.path.join(OUT, f"{name}.replay_T{T}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB")
+    del torch
 
 
 if __name__ == "__main__":
