@@ -110,7 +110,7 @@ class ReplayBuffer:
         env.emit_imposters = True
         self._env = env
         cur = env.flat_states()
-        seq = cur[:, None, :].expand(-1, self.trajectory_size, -1).contiguous()
+        seq = cur[:, None, :].repeat(1, self.trajectory_size, 1)  # a copy even for T == 1 (cur is overwritten every step)
         self._seq = [seq, torch.empty_like(seq)]
         self._cur_flat = cur
 
