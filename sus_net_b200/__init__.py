@@ -33,6 +33,7 @@ from .metrics import METRIC_ORDER, STAT_KEYS, SusMetrics  # noqa: F401
 from .distributed import reduce_episode_stats, shard_range  # noqa: F401
 from .host_pipeline import HostStepper  # noqa: F401
 from .replay_memory import Batch, ReplayBuffer  # noqa: F401
+from .train import BatchedActor, DQNTeamTrainer, ExponentialSchedule, allreduce_grads, train_batched  # noqa: F401
 
 # reference class names, for `from sus_net_b200 import FourRoomEnv` style drop-in use
 FourRoomEnv = BatchedFourRoomEnv

@@ -125,6 +125,7 @@ class SequenceStateFeaturizer:
         L.check(env.lib.sus_encode_shape(C.byref(env._cfg), C.byref(self._spec), C.byref(shape)))
         self._shape = shape
         self._sp_buf = self._ns_buf = None
+        self._buffers = {}  # n_items -> (spatial, non_spatial): acting (N envs) and training (batch) sizes alternate
         self.B = self.T = None
 
     def _make_spec(self):
@@ -132,10 +133,14 @@ class SequenceStateFeaturizer:
 
     def _alloc(self, n_items):
         sh, dev = self._shape, self.env.device
-        if self._ns_buf is None or self._ns_buf.shape[1] != n_items:
-            self._sp_buf = (torch.empty((sh.spatial_views, n_items, sh.spatial_floats), dtype=torch.float32, device=dev)
-                            if sh.spatial_views else None)
-            self._ns_buf = torch.empty((sh.non_spatial_views, n_items, sh.non_spatial_floats), dtype=torch.float32, device=dev)
+        if n_items not in self._buffers:
+            if len(self._buffers) >= 4:
+                self._buffers.pop(next(iter(self._buffers)))
+            sp = (torch.empty((sh.spatial_views, n_items, sh.spatial_floats), dtype=torch.float32, device=dev)
+                  if sh.spatial_views else None)
+            ns = torch.empty((sh.non_spatial_views, n_items, sh.non_spatial_floats), dtype=torch.float32, device=dev)
+            self._buffers[n_items] = (sp, ns)
+        self._sp_buf, self._ns_buf = self._buffers[n_items]
 
     def fit(self, state_sequence):
         """Featurize a (B, T, S) batch of flattened states (train.py:70-74,346-348) in one kernel launch."""

@@ -105,6 +105,7 @@ def main():
     replay_fixture("cfg4_base_1v4", T=1, M=100)
     replay_fixture("base_2v3_j3", T=3, M=64)
     replay_fixture("tagging_2v5_short", T=2, M=50)
+    train_step_fixture()
     if "--replay-only" in sys.argv:
         return
     for name in CASES:
@@ -168,6 +169,66 @@ def replay_fixture(name, T, M, n_envs=6, n_steps=45):
     np.savez_compressed(path, **out)
     print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB")
     del torch
+
+
+def train_step_fixture():
+    """The reference's DQNTeamTrainer.train_step (src/train.py:50-149) on a batch from its own ReplayBuffer with its
+    own MLP Q-networks and FlatFeaturizer: losses and updated weights are the known answers for the GPU trainer."""
+    import torch
+
+    H.import_reference()
+    from src.features import (AliveCrewFeaturizer, ClosestAliveCrewFeaturizer, CompositeFeaturizer, FlatFeaturizer,
+                              OneHotAgentPositionFeaturizer)
+    from src.models.dqn import MLP
+    from src.replay_memory import ReplayBuffer as RefReplay
+    from src.train import DQNTeamTrainer
+
+    name, T, M, n_envs, n_steps = "cfg4alt_itg_1v4", 2, 96, 8, 12
+    cfg = dict(CASES[name]); cfg["shuffle_imposter_index"] = True
+    ref = H.ReferenceBatch(cfg, n_envs, SEED, env_id_base=ENV_ID_BASE)
+    flat = ref.reset()
+    S = flat.shape[1]
+    buf = RefReplay(max_size=M, state_size=S, trajectory_size=T, n_agents=ref.A, n_imposters=1)
+    seqs = [np.repeat(flat[i][None].astype(np.float64), T, axis=0) for i in range(n_envs)]
+    for t in range(n_steps):
+        imps = [np.asarray(e.imposter_idxs).copy() for e in ref.envs]
+        a = ref.sample_actions()
+        o = ref.step(a)
+        cur = ref.flat_states()
+        for i in range(n_envs):
+            nxt = np.roll(seqs[i].copy(), -1, axis=0); nxt[-1] = o["next_flat"][i]
+            buf.add(state=seqs[i], action=a[i], reward=o["rewards"][i], next_state=nxt, done=bool(o["done"][i]), imposters=imps[i])
+            seqs[i] = np.repeat(cur[i][None].astype(np.float64), T, axis=0) if (o["done"][i] or o["trunc"][i]) else nxt
+    torch.manual_seed(7)
+    batch = buf.sample(48)
+    env = ref.envs[0]
+    feat = FlatFeaturizer(env, CompositeFeaturizer([OneHotAgentPositionFeaturizer(env), AliveCrewFeaturizer(env),
+                                                    ClosestAliveCrewFeaturizer(env)]))
+    F_ = 98 * T
+    torch.manual_seed(11)
+    imp_model, crew_model = MLP([F_, 32, 16, 6]), MLP([F_, 24, 5])
+    imp_target, crew_target = imp_model.create_copy(), crew_model.create_copy()
+    with torch.no_grad():  # make the targets differ from the online nets
+        for p_ in list(imp_target.parameters()) + list(crew_target.parameters()):
+            p_.add_(0.01 * torch.randn_like(p_))
+    before = {f"{n}.{k}": v.detach().clone().numpy() for n, m in (("imp", imp_model), ("crew", crew_model),
+              ("imp_target", imp_target), ("crew_target", crew_target)) for k, v in m.state_dict().items()}
+    trainer = DQNTeamTrainer(torch.optim.Adam(imp_model.parameters(), lr=1e-3),
+                             torch.optim.Adam(crew_model.parameters(), lr=1e-3), gamma=0.9)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        losses = trainer.train_step(batch, feat, imp_model, imp_target, crew_model, crew_target)
+    after = {f"{n}.{k}": v.detach().clone().numpy() for n, m in (("imp", imp_model), ("crew", crew_model))
+             for k, v in m.state_dict().items()}
+    out = dict(T=T, losses=np.array(losses, dtype=np.float64), states=batch.states.numpy(), actions=batch.actions.numpy(),
+               rewards=batch.rewards.numpy(), next_states=batch.next_states.numpy(), dones=batch.dones.numpy(),
+               imposters=batch.imposters.numpy())
+    out.update({f"before.{k}": v for k, v in before.items()})
+    out.update({f"after.{k}": v for k, v in after.items()})
+    path = os.path.join(OUT, "train_step.cfg4alt_flat98_T2.npz")
+    np.savez_compressed(path, **out)
+    print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB, losses {losses}")
 
 
 if __name__ == "__main__":
