@@ -81,7 +81,7 @@ def test_batched_training_loop_runs_and_acts_within_role_ranges(cuda_lib):
                              train_step_interval=5, target_update_interval=10, generator=gen)
     env.check_actions()  # every action the actor produced was inside its agent's role list
     assert len(losses) == 8 and all(np.isfinite(l).all() for l in losses)
-    assert buf.size == 8 * N and int(env.episode_stats()[8]) > 0
+    assert buf.size == 8 * N and int(env.metrics_batch()[:, 0].max()) == 40  # envs advanced 40 steps (fewer only where an episode restarted)
     # greedy acting (eps = 0): imposters pick argmax of the imposter net, dead agents keep action 0
     seq = buf.state_sequence
     feat.fit(seq)
