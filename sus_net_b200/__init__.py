@@ -29,7 +29,7 @@ from .featurizers import (  # noqa: F401
     StateFieldFeaturizer,
     WallsFeaturizer,
 )
-from .metrics import METRIC_ORDER, STAT_KEYS, SusMetrics  # noqa: F401
+from .metrics import METRIC_ORDER, STAT_KEYS, EpisodicMetricHandler, SusMetrics  # noqa: F401
 from .distributed import reduce_episode_stats, shard_range  # noqa: F401
 from .host_pipeline import HostStepper  # noqa: F401
 from .replay_memory import Batch, ReplayBuffer  # noqa: F401

@@ -53,3 +53,41 @@ class EnvMetricView:
         import json
 
         return json.dumps(self.get_metrics(), indent=4)
+
+
+class EpisodicMetricHandler:
+    """`EpisodicMetricHandler` (metrics.py:67-95) fed from the device-side finished-episode accumulators instead of
+    one `info` dict per episode: `compute()` returns the same per-episode averages the reference's
+    `sum(values) / len(values)` gives for the counters the env maintains; `save_metrics` writes them as JSON."""
+
+    def __init__(self):
+        self.totals = {k: 0 for k in STAT_KEYS}
+        self.extra = {}
+
+    def update_from_stats(self, stats):
+        """stats: (10,) int64 tensor / sequence in STAT_KEYS order (already reduced over ranks)."""
+        vals = stats.tolist() if hasattr(stats, "tolist") else list(stats)
+        self.totals = dict(zip(STAT_KEYS, (int(v) for v in vals)))
+
+    def set(self, metrics):
+        for k, v in metrics.items():
+            self.extra[str(k)] = v
+
+    def compute(self):
+        n = max(self.totals["episodes"], 1)
+        name_of = {"crew_won": SusMetrics.CREW_WON, "imposter_won": SusMetrics.IMPOSTER_WON,
+                   "imp_killed_crew": SusMetrics.IMP_KILLED_CREW, "completed_jobs": SusMetrics.COMPLETED_JOBS,
+                   "sabotaged_jobs": SusMetrics.SABOTAGED_JOBS, "imp_voted_out": SusMetrics.IMP_VOTED_OUT,
+                   "crew_voted_out": SusMetrics.CREW_VOTED_OUT, "total_time_steps": SusMetrics.TOTAL_TIME_STEPS}
+        out = {m: 0.0 for m in SusMetrics}
+        for k, m in name_of.items():
+            out[m] = self.totals[k] / n
+        return out
+
+    def save_metrics(self, save_file_path):
+        import json
+
+        with open(save_file_path, "w") as f:
+            json.dump({"episodes": self.totals["episodes"], "truncated_episodes": self.totals["truncated_episodes"],
+                       "totals": self.totals, "averages": {str(k): v for k, v in self.compute().items()},
+                       **self.extra}, f)

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: end-to-end batched DQN loop -- ImposterTrainingGround 1v4 (walled), FlatFeaturizer(OneHot +
+AliveCrew + ClosestAliveCrew) = 98 features, MLP imposter Q-net [98,256,128,64,16,6] vs a random crew
+(notebooks/experiment_1v1.ipynb cell 1 model args), T = 1, gamma = 0.9, lr = 1e-3, 131 072 envs per GPU, replay
+writes on the GPU.  One process per GPU (torchrun) or a single process.
+
+    python tools/train_demo.py [--envs-per-gpu 131072] [--iters 200]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/train_demo.py
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+from torch import nn  # noqa: E402
+
+import sus_net_b200 as S  # noqa: E402
+
+
+class MLPQ(nn.Module):
+    def __init__(self, dims):
+        super().__init__()
+        layers = []
+        for i, d in enumerate(dims[:-1]):
+            layers += [nn.Linear(d, dims[i + 1]), nn.PReLU()]
+        self.model = nn.Sequential(*layers[:-1])
+        self.dims = dims
+
+    def forward(self, spatial_x, non_spatial_x):
+        return self.model(non_spatial_x.reshape(spatial_x.size(0), -1))
+
+    def create_copy(self):
+        m = MLPQ(self.dims)
+        m.load_state_dict(self.state_dict())
+        return m
+
+
+class RandomQ(nn.Module):
+    """RandomEquiprobable (src/models/dqn.py:111-138) on the device."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.n = n
+
+    def forward(self, spatial_x, non_spatial_x):
+        b = spatial_x.size(0)
+        out = torch.zeros(b, self.n, device=spatial_x.device)
+        out[torch.arange(b, device=out.device), torch.randint(0, self.n, (b,), device=out.device)] = 1
+        return out
+
+    def create_copy(self):
+        return RandomQ(self.n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--batch", type=int, default=4096)
+    a = ap.parse_args()
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = a.envs_per_gpu
+    env = S.BatchedImposterTrainingGround(n_crew=4, n_jobs=0, time_step_reward=0, kill_reward=-3, sabotage_reward=0,
+                                          end_of_game_reward=0, num_envs=N, seed=7, env_id_base=rank * N, device=dev)
+    feat = S.FlatFeaturizer(env, S.CompositeFeaturizer([S.OneHotAgentPositionFeaturizer(env), S.AliveCrewFeaturizer(env),
+                                                        S.ClosestAliveCrewFeaturizer(env)]))
+    torch.manual_seed(0)  # identical initial weights on every rank
+    imp, crew = MLPQ([98, 256, 128, 64, 16, 6]).to(dev), RandomQ(5).to(dev)
+    trainer = S.DQNTeamTrainer(torch.optim.Adam(imp.parameters(), lr=1e-3), None, gamma=0.9)
+    buf = S.ReplayBuffer(8 * N, env.flattened_state_size, 1, env.n_agents, 1, device=dev)
+    sched = S.ExponentialSchedule(1.0, 0.05, a.iters)
+    S.train_batched(env, buf, feat, imp, crew, trainer, sched, num_iterations=10, batch_size=a.batch)  # warm-up
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    losses = S.train_batched(env, buf, feat, imp, crew, trainer, sched, num_iterations=a.iters, batch_size=a.batch)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    stats = S.reduce_episode_stats(env.episode_stats())
+    if rank == 0:
+        m = S.EpisodicMetricHandler(); m.update_from_stats(stats)
+        print(json.dumps({"config": "cfg5 batched DQN loop (acting + step + replay push + train every 5)",
+                          "n_gpus": world, "envs_per_gpu": N, "iterations": a.iters, "wall_s": dt,
+                          "env_steps_per_s_in_training_loop": world * N * a.iters / dt,
+                          "train_steps": len(losses), "last_losses": losses[-1],
+                          "episodes": int(stats[0]), "imposter_win_rate": float(stats[2]) / max(int(stats[0]), 1)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
