@@ -24,6 +24,7 @@ using namespace susnet;
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kTmaMaxWarps = 12;  // persistent TMA-path CTAs: up to 384 threads, one CTA per SM
 constexpr unsigned kFull = 0xffffffffu;
 
 thread_local std::string g_last_error;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepP
 // K1 (+K2), TMA path: persistent CTAs (one per SM), each warp walks groups of 32 envs; rewards, the replay-layout
 // state row and the feature tensors are staged in shared memory and leave the SM as TMA bulk stores.
 template <int VARIANT, bool ENCODE>
-__global__ void __launch_bounds__(kThreads, 1) k_step_tma(const __grid_constant__ StepParams p,
+__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_tma(const __grid_constant__ StepParams p,
                                                           const __grid_constant__ TileLayout L) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ GridTables tb;
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(kThreads) k_encode_rows(const __grid_constant_
 
 // K2, TMA path (see k_step_tma): persistent CTAs, features staged in shared memory, bulk stores.
 template <typename T, bool FROM_ROWS>
-__global__ void __launch_bounds__(kThreads, 1) k_encode_tma(const __grid_constant__ EncodeParams p,
+__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_encode_tma(const __grid_constant__ EncodeParams p,
                                                             const __grid_constant__ TileLayout L) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ GridTables tb;
@@ -670,10 +671,13 @@ bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool wa
     t.per_warp = off > 0 ? off : 128;
     const int budget = max_dyn_smem - 2048;  // static tables + slack
     t.warps = budget / t.per_warp;
-    if (t.warps > kThreads / 32) t.warps = kThreads / 32;
+    const char* env_mw = std::getenv("SUSNET_TILE_MAXWARPS");
+    const int max_warps = env_mw ? std::atoi(env_mw) : kTmaMaxWarps;
+    if (t.warps > max_warps) t.warps = max_warps;
+    if (t.warps > kTmaMaxWarps) t.warps = kTmaMaxWarps;
     if (force_w > 0 && force_w < t.warps) t.warps = force_w;
     if (t.warps > best.warps) best = t;
-    if (best.warps == kThreads / 32) break;
+    if (!force_g && best.warps >= 8) break;  // G = 8 tiles with >= 8 warps measured best; otherwise try G = 4
   }
   if (best.warps < 2) return false;
   const char* env_s = std::getenv("SUSNET_STAGGER_NS");
@@ -690,7 +694,13 @@ unsigned persistent_grid(int64_t n_items, const TileLayout& L, int sms) {
 
 template <typename K>
 int allow_big_smem(K kernel, size_t bytes) {
+  // one table per kernel instantiation, indexed by the current device: set the attribute only when it grows
+  static std::atomic<size_t> granted[64];
+  int dev = 0;
+  SUS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && bytes <= granted[dev].load()) return SUS_OK;
   SUS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (dev >= 0 && dev < 64) granted[dev].store(bytes);
   return SUS_OK;
 }
 

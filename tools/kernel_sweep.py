@@ -56,16 +56,18 @@ def main():
     out["memset_gbs_best"] = buf.numel() * 4 / (min(ts) * 1e-3) / 1e9
     out["memset_gbs_median"] = buf.numel() * 4 / (sorted(ts)[5] * 1e-3) / 1e9
     del buf
-    for g, w in [(8, 8), (4, 8), (8, 6), (8, 4), (4, 4), (16, 4), (16, 5)]:
+    os.environ["SUSNET_TILE_MAXWARPS"] = "12"
+    for g, w in [(8, 8), (4, 8), (4, 9), (4, 10), (4, 11), (8, 6)]:
         os.environ["SUSNET_TILE_G"], os.environ["SUSNET_TILE_WARPS"] = str(g), str(w)
         med, best = time_fused(N, a.steps)
         out[f"G{g}_W{w}"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
     os.environ.pop("SUSNET_TILE_G"); os.environ.pop("SUSNET_TILE_WARPS")
-    for st in (500, 1000, 1500, 2000, 2500, 3000, 4000):
+    os.environ.pop("SUSNET_TILE_MAXWARPS")
+    for st in ():
         os.environ["SUSNET_STAGGER_NS"] = str(st)
         med, best = time_fused(N, a.steps)
         out[f"stagger_{st}"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
-    os.environ.pop("SUSNET_STAGGER_NS")
+    os.environ.pop("SUSNET_STAGGER_NS", None)
     med, best = time_fused(N, a.steps, policy_fused=True)
     out["default_fused_policy"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
     for n in (1 << 16, 1 << 18, 1 << 22):
