@@ -12,8 +12,9 @@ auto-reset, Global feature tensors of the state the next action is taken from).
 
 Numbers on the JSON line
   value     whole-job env-steps/s with state and actions resident in HBM (CUDA events, max over ranks)
-  e2e       the same work driven through the public Python API with HOST buffers: per step the actions come from
-            pinned host memory (H2D) and rewards/dones/truncations go back to pinned host memory (D2H); the
+  e2e       the same work driven through the public Python API with HOST buffers: per step the actions (uint8
+            role-list indices) come from pinned host memory (H2D) and rewards/dones/truncations go back to pinned
+            host memory (D2H); the
             feature tensors stay on the device, where the Q-network consumes them
   roofline  achieved = 2650 algorithmic bytes per env-step x envs per launch / mean duration of the
             fused step+encode kernel, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
@@ -298,10 +299,10 @@ def run_b200_arm(args):
         # the same deterministic trajectory: same seed and env ids => identical states)
         rec = make_env()
         rec.reset()
-        host_actions = torch.empty((W + K, N, A), dtype=torch.int32).pin_memory()
+        host_actions = torch.empty((W + K, N, A), dtype=torch.uint8).pin_memory()  # role-list indices < 256
         for k in range(W + K):
             a = rec.sample_actions()
-            host_actions[k].copy_(a, non_blocking=True)
+            host_actions[k].copy_(a.to(torch.uint8), non_blocking=True)
             rec.step(a, featurizer=feat)
         torch.cuda.synchronize(dev)
         del rec
@@ -326,7 +327,7 @@ def run_b200_arm(args):
         # the same chain on ONE stream (no overlap between the copies and the kernel), for reference
         seq = make_env()
         seq.reset()
-        d_actions = torch.empty((N, A), dtype=torch.int32, device=dev)
+        d_actions = torch.empty((N, A), dtype=torch.uint8, device=dev)
 
         def seq_step(k):
             d_actions.copy_(host_actions[k], non_blocking=True)
@@ -347,7 +348,7 @@ def run_b200_arm(args):
                "h2d_bytes_per_step": world * stepper.h2d_bytes_per_step,
                "d2h_bytes_per_step": world * stepper.d2h_bytes_per_step,
                "single_stream_value": world * N * K / (seq_ms * 1e-3),
-               "note": "sus_net_b200.HostStepper: int32 actions H2D from pinned host memory, fused step+encode, rewards f32 "
+               "note": "sus_net_b200.HostStepper: uint8 actions H2D from pinned host memory, fused step+encode, rewards f32 "
                        "+ done + truncated D2H to pinned host memory every step (3 streams, 2 slots); feature tensors stay "
                        "in HBM for the Q-network"}
         del env, seq

@@ -6,12 +6,15 @@ import torch
 
 
 class HostStepper:
-    def __init__(self, env, featurizer=None, slots=2):
+    def __init__(self, env, featurizer=None, slots=2, actions_dtype=torch.uint8):
+        """actions_dtype: dtype of the host action rows (uint8 = 1 byte per agent on the PCIe link, role-list indices
+        are < 256; int32 / int64 are accepted too, the reference's loop uses np.int32)."""
         assert env.batched, "HostStepper drives batched envs"
         self.env, self.featurizer, self.slots = env, featurizer, slots
         dev, N, A = env.device, env.num_envs, env.n_agents
         self.s_h2d, self.s_run, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
-        self.d_actions = [torch.empty((N, A), dtype=torch.int32, device=dev) for _ in range(slots)]
+        assert actions_dtype in (torch.uint8, torch.int32, torch.int64)
+        self.d_actions = [torch.empty((N, A), dtype=actions_dtype, device=dev) for _ in range(slots)]
         self.d_out = [(torch.empty((N, A), dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.bool, device=dev),
                        torch.empty(N, dtype=torch.bool, device=dev)) for _ in range(slots)]
         self.h_out = [(torch.empty((N, A), dtype=torch.float32).pin_memory(), torch.empty(N, dtype=torch.bool).pin_memory(),
@@ -26,14 +29,14 @@ class HostStepper:
 
     @property
     def h2d_bytes_per_step(self):
-        return self.d_actions[0].numel() * 4
+        return self.d_actions[0].numel() * self.d_actions[0].element_size()
 
     @property
     def d2h_bytes_per_step(self):
         return sum(t.numel() * t.element_size() for t in self.d_out[0])
 
     def step(self, host_actions):
-        """Enqueue one step on `host_actions` ((N, A) int32, ideally pinned).  Returns the slot whose pinned host
+        """Enqueue one step on `host_actions` ((N, A) of `actions_dtype`, ideally pinned).  Returns the slot whose pinned host
         buffers `(rewards, dones, truncated)` will hold the results once `wait(slot)` returns."""
         slot = self.k % self.slots
         first_use = self.k < self.slots

@@ -303,7 +303,7 @@ def test_host_stepper_matches_direct_stepping(cuda_lib):
     acts, want = [], []
     for t in range(T):  # record a valid action stream and the expected results
         a = ref.sample_actions().clone()
-        acts.append(a.cpu().pin_memory())
+        acts.append(a.to(torch.uint8).cpu().pin_memory())
         _, r, d, tr, _ = ref.step(a)
         want.append((cpu(r).copy(), cpu(d).copy(), cpu(tr).copy()))
     feat = S.GlobalFeaturizer(env)
