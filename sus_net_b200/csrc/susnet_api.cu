@@ -13,11 +13,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "susnet_device.cuh"
 #include "susnet_encode.cuh"
 #include "susnet_tile.cuh"
+#include "susnet_ws.cuh"
 
 using namespace susnet;
 
@@ -146,31 +149,46 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ Rese
 struct StepInput {
   uint64_t pos, jobpos;
   uint4 aux, met;
-  uint64_t acts;  // one byte per agent
-  uint32_t oob;   // an action was negative or >= 256
+  uint32_t raw[SUS_MAX_AGENTS];  // action words exactly as loaded (no arithmetic here: consumers would stall on the loads)
+  uint32_t oob64;                // int64 actions only: a high word was non-zero
 };
 
 __device__ __forceinline__ void load_input(const StepParams& p, int64_t e, bool have, StepInput& in) {
-  in.pos = in.jobpos = in.acts = 0; in.oob = 0;
+  in.pos = in.jobpos = 0; in.oob64 = 0;
   in.aux = in.met = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < SUS_MAX_AGENTS; ++i) in.raw[i] = 0;
   if (!have) return;
   const int A = p.c.A;
   in.pos = p.st.pos[e]; in.jobpos = p.st.jobpos[e]; in.aux = p.st.aux[e]; in.met = p.st.met[e];
   if (p.actions == nullptr) return;
   if (p.actions_dtype == SUS_I32) {
-    const int32_t* a = static_cast<const int32_t*>(p.actions) + e * A;
-    for (int i = 0; i < A; ++i) { const uint32_t v = (uint32_t)a[i]; in.oob |= v & ~0xffu; in.acts |= (uint64_t)(v & 0xffu) << (8 * i); }
-  } else if (p.actions_dtype == SUS_I64) {
-    const long long* a = static_cast<const long long*>(p.actions) + e * A;
-    for (int i = 0; i < A; ++i) {
-      const unsigned long long v = (unsigned long long)a[i];
-      in.oob |= (v & ~0xffull) ? 1u << 8 : 0u;
-      in.acts |= (uint64_t)(v & 0xffull) << (8 * i);
-    }
-  } else {
+    const uint32_t* a = static_cast<const uint32_t*>(p.actions) + e * A;
+#pragma unroll
+    for (int i = 0; i < SUS_MAX_AGENTS; ++i)
+      if (i < A) in.raw[i] = a[i];
+  } else if (p.actions_dtype == SUS_U8) {
     const uint8_t* a = static_cast<const uint8_t*>(p.actions) + e * A;
-    for (int i = 0; i < A; ++i) in.acts |= (uint64_t)a[i] << (8 * i);
+#pragma unroll
+    for (int i = 0; i < SUS_MAX_AGENTS; ++i)
+      if (i < A) in.raw[i] = a[i];
+  } else {
+    const unsigned long long* a = static_cast<const unsigned long long*>(p.actions) + e * A;
+#pragma unroll
+    for (int i = 0; i < SUS_MAX_AGENTS; ++i)
+      if (i < A) { const unsigned long long v = a[i]; in.raw[i] = (uint32_t)v; in.oob64 |= (uint32_t)(v >> 32); }
   }
+}
+
+// one byte per agent + "some action was negative or >= 256"
+__device__ __forceinline__ uint64_t pack_actions(const StepInput& in, int A, bool& in_range) {
+  uint64_t acts = 0;
+  uint32_t oob = in.oob64;
+#pragma unroll
+  for (int i = 0; i < SUS_MAX_AGENTS; ++i)
+    if (i < A) { oob |= in.raw[i] & ~0xffu; acts |= (uint64_t)(in.raw[i] & 0xffu) << (8 * i); }
+  in_range = oob == 0;
+  return acts;
 }
 
 __device__ __forceinline__ void unpack_state(const StepInput& in, EnvState& s) {
@@ -194,15 +212,14 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
   if (!have) return;
   unpack_state(in, s);
   // ---- actions: role-list indices, one byte per agent
-  uint64_t acts = in.acts;
   bool ok = true;
+  uint64_t acts = pack_actions(in, A, ok);
   if (p.actions == nullptr) {  // fused random policy == env.step(env.sample_actions()), base.py:326-330
     WordStream wa;
     wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, p.tick, P_ACT_FUSED);
     for (int i = 0; i < A; ++i)
       acts |= (uint64_t)bounded(wa.word(i), n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) << (8 * i);
   } else {
-    ok = in.oob == 0;
     for (int i = 0; i < A; ++i)
       if (get_byte(acts, i) >= n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) ok = false;
     if (!ok) acts = 0;
@@ -368,6 +385,198 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_tma(const __grid_
     in = in_next;
   }
   em.finish();
+}
+
+// One plane sub-tile (8 envs) of the emitter warp: retire the store that last used this tile, clear the ones it
+// carried, set the new ones from the group's plane records with all 32 lanes, hand the tile to the TMA engine.
+template <int TE>  // envs per plane tile: 8 or 16
+struct EmitterTile {
+  static constexpr int NE = TE / 2;  // plane entries per lane: TE envs x 16 entries over 32 lanes
+  float* tile;
+  uint32_t prev[NE];  // float indices this lane set in the tile (0xffffffff = none)
+  bool inflight;
+};
+
+template <int TE, bool PERSPECTIVE>
+__device__ __forceinline__ void emit_sub(EmitterTile<TE>& t, EmitterTile<TE>& other, int& last_commit, int my_id,
+                                         const uint16_t* po, int g0, int cnt, int k, int A, int R, float* gdst, int lane) {
+  constexpr int NE = EmitterTile<TE>::NE;
+  if (t.inflight) {
+    if (lane == 0) {
+      if (last_commit != my_id) bulk_wait_read_all_but_newest();  // the newest group reads the other tile
+      else bulk_wait_read_all();
+    }
+    if (last_commit == my_id) other.inflight = false;
+    t.inflight = false;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < NE; ++r)
+    if (t.prev[r] != 0xffffffffu) t.tile[t.prev[r]] = 0.0f;
+  const int gc = cnt - g0 < TE ? cnt - g0 : TE;
+  const int el = lane & (TE - 1);
+  const uint16_t* rec = po + (g0 + el) * 16 + lane / TE;
+  uint32_t off[NE];
+#pragma unroll
+  for (int r = 0; r < NE; ++r) off[r] = el < gc ? (uint32_t)rec[(32 / TE) * r] : 0x3ffu;  // all loads first
+#pragma unroll
+  for (int r = 0; r < NE; ++r) {
+    if (off[r] != 0x3ffu) {
+      if (PERSPECTIVE) {
+        const int q = lane / TE + (32 / TE) * r;
+        if (k > 0 && q < A) off[r] += (uint32_t)((persp_channel_of_agent(k, q) - q) * 81);  // view k's channel order
+      }
+      const uint32_t idx = (uint32_t)(el * R) + off[r];
+      t.tile[idx] = 1.0f;
+      t.prev[r] = idx;
+    } else {
+      t.prev[r] = 0xffffffffu;
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (drain(gdst, t.tile, (uint32_t)(gc * R * 4), lane)) {
+    if (lane == 0) bulk_commit();
+    t.inflight = true;
+    last_commit = my_id;
+  }
+}
+
+// the emitter warp's loop over the groups its CTA's compute warps produce
+template <int TE, bool PERSPECTIVE>
+__device__ __forceinline__ void emitter_loop(const StepParams& p, const WsLayout& L, uint8_t* dyn_smem, uint64_t* bars,
+                                             int64_t n_groups, int64_t g_stride, int lane) {
+  constexpr int NE = EmitterTile<TE>::NE;
+  const int CW = L.compute_warps, A = p.c.A, R = p.enc.sp_floats;
+  EmitterTile<TE> t0, t1;
+  t0.tile = reinterpret_cast<float*>(dyn_smem);
+  t1.tile = reinterpret_cast<float*>(dyn_smem + L.tile_bytes);
+  t0.inflight = t1.inflight = false;
+#pragma unroll
+  for (int r = 0; r < NE; ++r) t0.prev[r] = t1.prev[r] = 0xffffffffu;
+  int last_commit = -1;
+  const int sp_views = PERSPECTIVE ? A : 1;
+  const int64_t base_g = (int64_t)blockIdx.x * CW;
+  for (int it = 0; base_g + (int64_t)it * g_stride < n_groups; ++it) {
+    const int sl = it & 1;
+    for (int w = 0; w < CW; ++w) {
+      const int64_t g = base_g + w + (int64_t)it * g_stride;
+      if (g >= n_groups) break;
+      const uint8_t* slot = dyn_smem + L.slots_off + (size_t)(w * 2 + sl) * L.slot_bytes;
+      mbar_wait(&bars[w * 2 + sl], (uint32_t)((it >> 1) & 1));
+      const int64_t e0 = g << 5;
+      const int64_t rem = p.N - e0;
+      const int cnt = rem < 32 ? (int)rem : 32;
+      const uint16_t* po = reinterpret_cast<const uint16_t*>(slot + L.po_off);
+      for (int k = 0; k < sp_views; ++k) {
+        float* gbase = p.spatial + ((int64_t)k * p.N + e0) * R;
+        for (int g0 = 0; g0 < cnt; g0 += 2 * TE) {
+          emit_sub<TE, PERSPECTIVE>(t0, t1, last_commit, 0, po, g0, cnt, k, A, R, gbase + (int64_t)g0 * R, lane);
+          if (g0 + TE < cnt)
+            emit_sub<TE, PERSPECTIVE>(t1, t0, last_commit, 1, po, g0 + TE, cnt, k, A, R, gbase + (int64_t)(g0 + TE) * R, lane);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[2 * CW + w * 2 + sl]);  // the slot may be refilled
+    }
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+// K1+K2, warp-specialised TMA path (susnet_ws.cuh): CW compute warps + one emitter warp per persistent CTA.
+template <int VARIANT>
+__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_ws(const __grid_constant__ StepParams p,
+                                                                  const __grid_constant__ WsLayout L) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const DevConfig& c = p.c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int CW = L.compute_warps, A = c.A, R = p.enc.sp_floats, F = p.enc.ns_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + L.bars_off);  // full[w*2+s], then empty[w*2+s]
+  {
+    float4* t = reinterpret_cast<float4*>(dyn_smem);
+    for (int i = threadIdx.x; i < (2 * L.tile_bytes) >> 4; i += blockDim.x) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 4 * CW; ++i) mbar_init(&bars[i], 1);
+  }
+  __syncthreads();
+  const int64_t n_groups = (p.N + 31) >> 5;
+  const int64_t g_stride = (int64_t)gridDim.x * CW;
+  const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
+  if (warp < CW) {
+    // ------------------------------------------------------------------ compute warp
+    int64_t g = (int64_t)blockIdx.x * CW + warp;
+    StepInput in, in_next;
+    load_input(p, (g << 5) + lane, g < n_groups && (g << 5) + lane < p.N, in);
+    for (int it = 0; g < n_groups; ++it, g += g_stride) {
+      const int64_t e0 = g << 5, e = e0 + lane;
+      const bool have = e < p.N;
+      const int64_t rem = p.N - e0;
+      const int cnt = rem < 32 ? (int)rem : 32;
+      {
+        const int64_t gn = g + g_stride, en = (gn << 5) + lane;
+        load_input(p, en, gn < n_groups && en < p.N, in_next);
+      }
+      const int sl = it & 1;
+      uint8_t* slot = dyn_smem + L.slots_off + (size_t)(warp * 2 + sl) * L.slot_bytes;
+      if (it >= 2) {
+        mbar_wait(&bars[2 * CW + warp * 2 + sl], (uint32_t)(((it >> 1) - 1) & 1));  // emitter is done with the slot
+        if (lane == 0) bulk_wait_read_all_but_newest();  // my dense stores of two groups ago have been read
+        __syncwarp();
+      }
+      bool stepped, finished;
+      EnvState s = {};
+      StepResult r = {};
+      uint8_t* rew = slot + L.rew_off;
+      float* nf = reinterpret_cast<float*>(slot + L.nf_off);
+      step_one<VARIANT>(p, tb, e, have, in, p.rewards ? rew + lane * A * rew_elem : nullptr,
+                        p.next_flat ? nf + lane * c.S : nullptr, s, r, stepped, finished);
+      finish_one(p, tb, e, lane, s, r, stepped, finished);
+      const ObsState o = obs_of(s);
+      float* ns = reinterpret_cast<float*>(slot + L.ns_off);
+      if (have) {
+        if (p.enc.kind == SUS_ENCODE_GLOBAL) global_ns_rows(c, o, ns + lane * F, 32 * F);
+        else
+          for (int k = 0; k < A; ++k) persp_ns_row(c, o, k, ns + (k * 32 + lane) * F);
+      }
+      write_plane_record(c, o, have, reinterpret_cast<uint16_t*>(slot + L.po_off) + lane * 16);
+      const bool all_stepped = __all_sync(kFull, stepped || !have);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (all_stepped) {
+        if (p.rewards) drain(static_cast<uint8_t*>(p.rewards) + e0 * A * rew_elem, rew, (uint32_t)(cnt * A * rew_elem), lane);
+        if (p.next_flat) drain(p.next_flat + e0 * c.S, nf, (uint32_t)(cnt * c.S * 4), lane);
+      } else if (stepped) {  // rare: an env of the group had its actions rejected; publish row by row
+        if (p.rewards) {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(rew + lane * A * rew_elem);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.rewards) + e * A * rew_elem);
+          for (int i = 0; i < A * rew_elem / 4; ++i) dst[i] = src[i];
+        }
+        if (p.next_flat)
+          for (int i = 0; i < c.S; ++i) p.next_flat[e * c.S + i] = nf[lane * c.S + i];
+      }
+      for (int k = 0; k < A; ++k)
+        drain(p.non_spatial + ((int64_t)k * p.N + e0) * F, ns + k * 32 * F, (uint32_t)(cnt * F * 4), lane);
+      __syncwarp();
+      if (lane == 0) {
+        bulk_commit();                     // one (possibly empty) DENSE group per group of envs
+        mbar_arrive(&bars[warp * 2 + sl]);  // plane records are ready for the emitter
+      }
+      in = in_next;
+    }
+    if (lane == 0) bulk_wait_all();
+  } else if (warp == CW) {
+    // ------------------------------------------------------------------ emitter warp
+    const bool persp = p.enc.kind == SUS_ENCODE_PERSPECTIVE;
+    if (L.tile_envs == 16) {
+      if (persp) emitter_loop<16, true>(p, L, dyn_smem, bars, n_groups, g_stride, lane);
+      else emitter_loop<16, false>(p, L, dyn_smem, bars, n_groups, g_stride, lane);
+    } else {
+      if (persp) emitter_loop<8, true>(p, L, dyn_smem, bars, n_groups, g_stride, lane);
+      else emitter_loop<8, false>(p, L, dyn_smem, bars, n_groups, g_stride, lane);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) k_sample_actions(const __grid_constant__ ActParams p) {
@@ -686,21 +895,70 @@ bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool wa
   return true;
 }
 
+// Warp-specialised layout (susnet_ws.cuh); returns false if it does not apply or does not fit.
+bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, WsLayout& L) {
+  if (enc.sp_floats <= 0 || (enc.kind != SUS_ENCODE_GLOBAL && enc.kind != SUS_ENCODE_PERSPECTIVE)) return false;
+  WsLayout t = {};
+  const char* env_te = std::getenv("SUSNET_WS_TILE");
+  t.tile_envs = (env_te && std::atoi(env_te) == 8) ? 8 : 16;
+  t.tile_bytes = align128((int64_t)t.tile_envs * enc.sp_floats * 4);
+  if (t.tile_envs == 16 && max_dyn_smem - 2048 - 2 * t.tile_bytes - 512 < 4 * (32 * 32 + align128((int64_t)c.A * 32 * enc.ns_floats * 4) + align128((int64_t)32 * c.A * rew_elem))) {
+    t.tile_envs = 8;  // big configs: fall back to 8-env tiles so that at least two compute warps fit
+    t.tile_bytes = align128((int64_t)8 * enc.sp_floats * 4);
+  }
+  int off = 0;
+  t.po_off = off; off += 32 * 32;
+  t.ns_off = off; off += align128((int64_t)c.A * 32 * enc.ns_floats * 4);
+  t.rew_off = off; off += align128((int64_t)32 * c.A * rew_elem);
+  t.nf_off = off; off += want_nf ? align128((int64_t)32 * c.S * 4) : 0;
+  t.slot_bytes = off;
+  const int budget = max_dyn_smem - 2048 - 2 * t.tile_bytes - 512;
+  int cw = budget / (2 * t.slot_bytes);
+  if (cw > kTmaMaxWarps - 1) cw = kTmaMaxWarps - 1;
+  const char* env_w = std::getenv("SUSNET_WS_WARPS");
+  if (env_w && std::atoi(env_w) > 0 && std::atoi(env_w) < cw) cw = std::atoi(env_w);
+  if (cw < 2) return false;
+  t.compute_warps = cw;
+  t.slots_off = 2 * t.tile_bytes;
+  t.bars_off = t.slots_off + 2 * cw * t.slot_bytes;
+  t.total_bytes = t.bars_off + 4 * cw * 8;
+  L = t;
+  return true;
+}
+
+// SUSNET_PATH: "direct" = register/LSU stores, "tma" = every warp stages and stores its own tiles,
+// "ws" (default) = warp-specialised emitter where planes are written, "tma" elsewhere.
+bool want_ws() {
+  const char* v = std::getenv("SUSNET_PATH");
+  return !v || std::strcmp(v, "ws") == 0;
+}
+
 unsigned persistent_grid(int64_t n_items, const TileLayout& L, int sms) {
   const int64_t groups = (n_items + 31) / 32;
   const int64_t ctas = (groups + L.warps - 1) / L.warps;
   return (unsigned)(ctas < sms ? ctas : sms);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel and per device: remember what was granted so the
+// attribute is only set when it has to grow (keyed by the kernel's address; instantiations share a pointer TYPE).
 template <typename K>
 int allow_big_smem(K kernel, size_t bytes) {
-  // one table per kernel instantiation, indexed by the current device: set the attribute only when it grows
-  static std::atomic<size_t> granted[64];
+  struct Entry { const void* fn; int dev; size_t bytes; };
+  static std::mutex mu;
+  static std::vector<Entry> granted;
   int dev = 0;
   SUS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && bytes <= granted[dev].load()) return SUS_OK;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> lock(mu);
+  for (Entry& en : granted)
+    if (en.fn == key && en.dev == dev) {
+      if (bytes <= en.bytes) return SUS_OK;
+      SUS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      en.bytes = bytes;
+      return SUS_OK;
+    }
   SUS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  if (dev >= 0 && dev < 64) granted[dev].store(bytes);
+  granted.push_back({key, dev, bytes});
   return SUS_OK;
 }
 
@@ -842,6 +1100,29 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   TileLayout L;
   // step-only launches move < 100 B per env and are latency/issue bound: the one-thread-per-env kernel with its
   // higher occupancy wins there (measured 14.6e9 vs 7.3e9 env-steps/s); the TMA path pays off once features are written
+  WsLayout W;
+  if (want_ws() && enc && make_ws_layout(p.c, p.enc, io->rewards_dtype == SUS_F64 ? 8 : 4, io->next_flat != nullptr,
+                                         di.max_dyn_smem, W)) {
+    const int64_t groups = (e->N + 31) / 32;
+    const int64_t ctas = (groups + W.compute_warps - 1) / W.compute_warps;
+    const unsigned gr = (unsigned)(ctas < di.sms ? ctas : di.sms);
+    const unsigned threads = (unsigned)(W.compute_warps + 1) * 32;
+    switch (e->cfg.variant) {
+      case SUS_VARIANT_BASE:
+        if (int rc = allow_big_smem(k_step_ws<SUS_VARIANT_BASE>, W.total_bytes)) return rc;
+        k_step_ws<SUS_VARIANT_BASE><<<gr, threads, W.total_bytes, st>>>(p, W);
+        break;
+      case SUS_VARIANT_TAGGING:
+        if (int rc = allow_big_smem(k_step_ws<SUS_VARIANT_TAGGING>, W.total_bytes)) return rc;
+        k_step_ws<SUS_VARIANT_TAGGING><<<gr, threads, W.total_bytes, st>>>(p, W);
+        break;
+      default:
+        if (int rc = allow_big_smem(k_step_ws<SUS_VARIANT_TRAINING_GROUND>, W.total_bytes)) return rc;
+        k_step_ws<SUS_VARIANT_TRAINING_GROUND><<<gr, threads, W.total_bytes, st>>>(p, W);
+        break;
+    }
+    return after_launch("k_step_ws");
+  }
   if (want_tma() && enc &&
       make_layout(p.c, p.enc, io->rewards_dtype == SUS_F64 ? 8 : 4, io->next_flat != nullptr, di.max_dyn_smem, L)) {
     const size_t smem = (size_t)L.per_warp * L.warps;

@@ -13,10 +13,10 @@ from tests.util import CASES, case_of, flat_featurizer, golden_files, load, make
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tma", "direct"], autouse=True)
+@pytest.fixture(params=["ws", "tma", "direct"], autouse=True)
 def store_path(request, monkeypatch):
-    """Every GPU test runs on both output paths of the kernels: shared-memory staging + TMA bulk stores (default)
-    and direct register stores (the fallback for ragged / unaligned outputs)."""
+    """Every GPU test runs on all output paths of the kernels: warp-specialised emitter + TMA bulk stores (default where
+    planes are written), per-warp staging + TMA bulk stores, and direct register stores (the fallback)."""
     monkeypatch.setenv("SUSNET_PATH", request.param)
     return request.param
 

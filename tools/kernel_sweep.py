@@ -56,18 +56,25 @@ def main():
     out["memset_gbs_best"] = buf.numel() * 4 / (min(ts) * 1e-3) / 1e9
     out["memset_gbs_median"] = buf.numel() * 4 / (sorted(ts)[5] * 1e-3) / 1e9
     del buf
-    os.environ["SUSNET_TILE_MAXWARPS"] = "12"
-    for g, w in [(8, 8), (4, 8), (4, 9), (4, 10), (4, 11), (8, 6)]:
+    os.environ["SUSNET_PATH"] = "tma"
+    for g, w in [(8, 8), (4, 8)]:
         os.environ["SUSNET_TILE_G"], os.environ["SUSNET_TILE_WARPS"] = str(g), str(w)
         med, best = time_fused(N, a.steps)
-        out[f"G{g}_W{w}"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
+        out[f"tma_G{g}_W{w}"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
     os.environ.pop("SUSNET_TILE_G"); os.environ.pop("SUSNET_TILE_WARPS")
-    os.environ.pop("SUSNET_TILE_MAXWARPS")
-    for st in ():
-        os.environ["SUSNET_STAGGER_NS"] = str(st)
-        med, best = time_fused(N, a.steps)
-        out[f"stagger_{st}"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
-    os.environ.pop("SUSNET_STAGGER_NS", None)
+    os.environ["SUSNET_PATH"] = "direct"
+    med, best = time_fused(N, a.steps)
+    out["direct"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
+    os.environ["SUSNET_PATH"] = "ws"
+    for te in (16, 8):
+        os.environ["SUSNET_WS_TILE"] = str(te)
+        for cw in (8, 7, 6, 5, 4):
+            os.environ["SUSNET_WS_WARPS"] = str(cw)
+            med, best = time_fused(N, a.steps)
+            out[f"ws_T{te}_CW{cw}"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
+    os.environ.pop("SUSNET_WS_TILE")
+    os.environ.pop("SUSNET_WS_WARPS")
+    os.environ.pop("SUSNET_PATH")
     med, best = time_fused(N, a.steps, policy_fused=True)
     out["default_fused_policy"] = {"median_ms": med, "best_ms": best, "gbs_algorithmic": 2650 * N / (med * 1e-3) / 1e9}
     for n in (1 << 16, 1 << 18, 1 << 22):
