@@ -45,8 +45,8 @@ UNIT = "env-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -143,51 +143,75 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread (the timed region
+    is tens of milliseconds, too short for `nvidia-smi -lms`); falls back to nvidia-smi if NVML is unavailable."""
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.lines = []
-        self.proc = None
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, torch_device):
+        self.samples = []  # (t, sm_mhz, reasons_mask)
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+        self.h = None
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(torch_device).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:  # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.h = None
+        self.index = torch_device.index
+
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(get_reasons(self.h))))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self, t_begin, t_end):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ts, line in self.lines:
-            if ts < t_begin - 0.05 or ts > t_end + 0.15:
-                continue
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        inside = [(mhz, r) for (t, mhz, r) in self.samples if t_begin <= t <= t_end]
+        if not inside:
+            return self._smi_fallback()
+        mask = 0
+        for _, r in inside:
+            mask |= r
+        return {"sm_mhz": statistics.median(m for m, _ in inside), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(name for bit, name in self.REASONS.items() if mask & bit), "samples": len(inside),
+                "source": "NVML polled every 2 ms inside the timed region"}
+
+    def _smi_fallback(self):
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]),
+                    "reasons": [n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")], "samples": 1,
+                    "source": "nvidia-smi right after the timed region (NVML polling unavailable)"}
+        except Exception:  # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -227,7 +251,7 @@ def run_b200_arm(args):
     env.reset()
     for _ in range(W):
         env.step(env.sample_actions(), featurizer=feat)
-    sampler = ClockSampler(dev.index)
+    sampler = ClockSampler(dev)
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     barrier()
