@@ -287,7 +287,7 @@ def run_b200_arm(args):
         except Exception:  # noqa: BLE001
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_step<BASE, encode=GLOBAL>", "kernel_ms": kern_ms,
+                "traffic": traffic, "kernel": "k_step_ws<BASE> (fused step + Global encode, warp-specialised TMA path)", "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_env_step": ALGO_BYTES_STEP_ENCODE, "peak_source": peak_src}
 
     # extra (not the headline): the same step with the random policy fused into the step kernel (one launch)

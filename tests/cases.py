@@ -40,3 +40,26 @@ FLAT_COMPONENT_SETS = {
     "cfg4_base_1v4": [["onehot_pos", "state_alive", "state_job_status", "walls", "rooms", "l1_crew", "closest_crew",
                        "dist_to_imposter", "scent", "coords", "alive_crew"]],
 }
+
+
+def random_case(rng):
+    """A random but valid constructor-argument set (any variant, sizes up to the build's limits, integer AND
+    non-integer reward constants, short episodes / vote windows so that every branch fires often)."""
+    variant = ("base", "tagging", "training_ground")[int(rng.integers(0, 3))]
+    n_imp = 1 if variant == "training_ground" else int(rng.integers(1, 4))
+    n_crew = int(rng.integers(max(1, n_imp + (variant != "training_ground")), 9 - n_imp))
+    n_jobs = int(rng.integers(1 if variant == "tagging" else 0, 9))
+
+    def reward():
+        v = float(rng.integers(-6, 7))
+        return v if rng.random() < 0.5 else v + float(rng.choice([0.1, 0.25, -0.3, 1.0 / 3.0]))
+
+    cfg = default_config(
+        variant, n_imposters=n_imp, n_crew=n_crew, n_jobs=n_jobs, include_walls=bool(rng.integers(0, 2)),
+        is_action_order_random=bool(rng.integers(0, 2)), shuffle_imposter_index=bool(rng.integers(0, 2)),
+        max_time_steps=int(rng.integers(5, 80)), tag_reset_interval=int(rng.integers(1, 12)),
+        kill_reward=reward(), complete_job_reward=reward(), sabotage_reward=reward(), time_step_reward=reward(),
+        game_end_reward=reward(), dead_penalty=reward(), vote_reward=reward())
+    if variant == "training_ground":  # pred_prey.py:52-66 fixes these
+        cfg.update(dead_penalty=0.0, is_action_order_random=False, complete_job_reward=3.0, max_time_steps=1000)
+    return cfg

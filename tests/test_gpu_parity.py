@@ -325,3 +325,42 @@ def test_host_stepper_matches_direct_stepping(cuda_lib):
     sp, ns = oracle.encode_global(cfg, cpu(env.flat_states(torch.int64)))
     views = feat.generate_featurized_states()
     assert np.array_equal(cpu(views[0][0])[:, 0], sp) and np.array_equal(cpu(views[3][1])[:, 0], ns[3])
+
+
+@pytest.mark.parametrize("k", range(16))
+def test_random_constructor_arguments_match_oracle(cuda_lib, k):
+    """Random variants / sizes / NON-INTEGER reward constants (the oracle is pinned against the reference on the same
+    generator: profiles/r01_oracle_pin_random_configs.log).  Rewards are compared as float64 bit patterns."""
+    import sus_net_b200 as S
+    from tests.cases import random_case
+
+    cfg = random_case(np.random.default_rng(100000 + k))
+    N, T = 777, 90
+    env = make_cuda_env(cfg, N, seed=k, env_id_base=50 * k)
+    if cfg["variant"] == "training_ground":
+        assert cfg["max_time_steps"] == 1000
+    env._rewards = torch.zeros((N, env.n_agents), dtype=torch.float64, device=env.device)
+    env._metrics_buf = torch.zeros((N, 8), dtype=torch.int64, device=env.device)
+    orc = oracle.OracleEnv(cfg, N, seed=k, env_id_base=50 * k)
+    env.reset(); orc.reset()
+    feat = None
+    if cfg["n_jobs"] > 0:
+        feat = S.PerspectiveFeaturizer(env) if k % 2 else S.GlobalFeaturizer(env)
+    for t in range(T):
+        nf, r, d, tr, _ = env.step(None, featurizer=feat)
+        o = orc.step(None)
+        assert np.array_equal(cpu(nf).astype(np.int64), o["next_flat"]), f"state differs at step {t}: {cfg}"
+        assert np.array_equal(reward_bits(cpu(r)), reward_bits(o["rewards"])), f"rewards differ at step {t}: {cfg}"
+        assert np.array_equal(cpu(d), o["done"] != 0) and np.array_equal(cpu(tr), o["trunc"] != 0)
+        assert np.array_equal(cpu(env._metrics_buf), o["metrics"])
+    cur = orc.flat_states()
+    assert np.array_equal(cpu(env.flat_states(torch.int64)), cur)
+    assert np.array_equal(cpu(env.episode_stats()), orc.stats())
+    if feat is not None:
+        views = feat.generate_featurized_states()
+        if k % 2:
+            sp, ns = oracle.encode_perspective(cfg, cur)
+            assert all(np.array_equal(cpu(v[0])[:, 0], sp[i]) and np.array_equal(cpu(v[1])[:, 0], ns[i]) for i, v in enumerate(views))
+        else:
+            sp, ns = oracle.encode_global(cfg, cur)
+            assert all(np.array_equal(cpu(v[0])[:, 0], sp) and np.array_equal(cpu(v[1])[:, 0], ns[i]) for i, v in enumerate(views))

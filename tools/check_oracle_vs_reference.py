@@ -76,7 +76,13 @@ def run_case(args):
     from oracle import ref_harness as H
 
     oracle.set_threads(1)
-    cfg = CASES[name]
+    if isinstance(name, tuple):  # ("random", k): k-th random constructor-argument set
+        from tests.cases import random_case
+
+        cfg = random_case(np.random.default_rng(100000 + name[1]))
+        name = f"random{name[1]}:{cfg['variant']}:{cfg['n_imposters']}v{cfg['n_crew']}j{cfg['n_jobs']}"
+    else:
+        cfg = CASES[name]
     ref = H.ReferenceBatch(cfg, n_envs, seed, env_id_base=base)
     orc = oracle.OracleEnv(cfg, n_envs, seed, env_id_base=base)
     f_ref, f_orc = ref.reset(), orc.reset()
@@ -116,8 +122,11 @@ def main():
     ap.add_argument("--procs", type=int, default=os.cpu_count())
     ap.add_argument("--seed", type=int, default=20260)
     ap.add_argument("--shards", type=int, default=1, help="independent env-id shards per case")
+    ap.add_argument("--random-configs", type=int, default=0, help="check this many random constructor-argument sets instead")
     a = ap.parse_args()
     names = [a.case] if a.case else list(CASES)
+    if a.random_configs:
+        names = [("random", k) for k in range(a.random_configs)]
     jobs = [(n, a.envs, a.steps, a.seed, s * a.envs) for n in names for s in range(a.shards)]
     t0 = time.time()
     with mp.Pool(a.procs) as pool:
