@@ -444,10 +444,10 @@ __device__ __forceinline__ void emit_sub(EmitterTile<TE>& t, EmitterTile<TE>& ot
 
 // the emitter warp's loop over the groups its CTA's compute warps produce
 template <int TE, bool PERSPECTIVE>
-__device__ __forceinline__ void emitter_loop(const StepParams& p, const WsLayout& L, uint8_t* dyn_smem, uint64_t* bars,
-                                             int64_t n_groups, int64_t g_stride, int lane) {
+__device__ __forceinline__ void emitter_loop(int A, int R, int64_t N, float* __restrict__ spatial, const WsLayout& L,
+                                             uint8_t* dyn_smem, uint64_t* bars, int64_t n_groups, int64_t g_stride, int lane) {
   constexpr int NE = EmitterTile<TE>::NE;
-  const int CW = L.compute_warps, A = p.c.A, R = p.enc.sp_floats;
+  const int CW = L.compute_warps;
   EmitterTile<TE> t0, t1;
   t0.tile = reinterpret_cast<float*>(dyn_smem);
   t1.tile = reinterpret_cast<float*>(dyn_smem + L.tile_bytes);
@@ -465,11 +465,11 @@ __device__ __forceinline__ void emitter_loop(const StepParams& p, const WsLayout
       const uint8_t* slot = dyn_smem + L.slots_off + (size_t)(w * 2 + sl) * L.slot_bytes;
       mbar_wait(&bars[w * 2 + sl], (uint32_t)((it >> 1) & 1));
       const int64_t e0 = g << 5;
-      const int64_t rem = p.N - e0;
+      const int64_t rem = N - e0;
       const int cnt = rem < 32 ? (int)rem : 32;
       const uint16_t* po = reinterpret_cast<const uint16_t*>(slot + L.po_off);
       for (int k = 0; k < sp_views; ++k) {
-        float* gbase = p.spatial + ((int64_t)k * p.N + e0) * R;
+        float* gbase = spatial + ((int64_t)k * N + e0) * R;
         for (int g0 = 0; g0 < cnt; g0 += 2 * TE) {
           emit_sub<TE, PERSPECTIVE>(t0, t1, last_commit, 0, po, g0, cnt, k, A, R, gbase + (int64_t)g0 * R, lane);
           if (g0 + TE < cnt)
@@ -481,6 +481,18 @@ __device__ __forceinline__ void emitter_loop(const StepParams& p, const WsLayout
     }
   }
   if (lane == 0) bulk_wait_all();
+}
+
+__device__ __forceinline__ void emitter_dispatch(bool persp, int A, int R, int64_t N, float* spatial, const WsLayout& L,
+                                                 uint8_t* dyn_smem, uint64_t* bars, int64_t n_groups, int64_t g_stride,
+                                                 int lane) {
+  if (L.tile_envs == 16) {
+    if (persp) emitter_loop<16, true>(A, R, N, spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+    else emitter_loop<16, false>(A, R, N, spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+  } else {
+    if (persp) emitter_loop<8, true>(A, R, N, spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+    else emitter_loop<8, false>(A, R, N, spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+  }
 }
 
 // K1+K2, warp-specialised TMA path (susnet_ws.cuh): CW compute warps + one emitter warp per persistent CTA.
@@ -568,14 +580,7 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_ws(const __grid_c
     if (lane == 0) bulk_wait_all();
   } else if (warp == CW) {
     // ------------------------------------------------------------------ emitter warp
-    const bool persp = p.enc.kind == SUS_ENCODE_PERSPECTIVE;
-    if (L.tile_envs == 16) {
-      if (persp) emitter_loop<16, true>(p, L, dyn_smem, bars, n_groups, g_stride, lane);
-      else emitter_loop<16, false>(p, L, dyn_smem, bars, n_groups, g_stride, lane);
-    } else {
-      if (persp) emitter_loop<8, true>(p, L, dyn_smem, bars, n_groups, g_stride, lane);
-      else emitter_loop<8, false>(p, L, dyn_smem, bars, n_groups, g_stride, lane);
-    }
+    emitter_dispatch(p.enc.kind == SUS_ENCODE_PERSPECTIVE, A, R, p.N, p.spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
   }
 }
 
@@ -678,6 +683,74 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_encode_tma(const __gri
                     false);
   }
   em.finish();
+}
+
+// K2, warp-specialised (see k_step_ws): compute warps unflatten rows / load env state and leave plane records + dense
+// rows; the emitter warp writes the plane tiles.
+template <typename T, bool FROM_ROWS>
+__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_encode_ws(const __grid_constant__ EncodeParams p,
+                                                                    const __grid_constant__ WsLayout L) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const DevConfig& c = p.c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int CW = L.compute_warps, A = c.A, R = p.enc.sp_floats, F = p.enc.ns_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + L.bars_off);
+  {
+    float4* t = reinterpret_cast<float4*>(dyn_smem);
+    for (int i = threadIdx.x; i < (2 * L.tile_bytes) >> 4; i += blockDim.x) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 4 * CW; ++i) mbar_init(&bars[i], 1);
+  }
+  __syncthreads();
+  const int64_t n_groups = (p.n_items + 31) >> 5;
+  const int64_t g_stride = (int64_t)gridDim.x * CW;
+  if (warp < CW) {
+    int it = 0;
+    for (int64_t g = (int64_t)blockIdx.x * CW + warp; g < n_groups; g += g_stride, ++it) {
+      const int64_t e0 = g << 5, e = e0 + lane;
+      const bool have = e < p.n_items;
+      const int64_t rem = p.n_items - e0;
+      const int cnt = rem < 32 ? (int)rem : 32;
+      ObsState o = {};
+      if (have) {
+        if (FROM_ROWS) {
+          o = parse_row<T>(c, static_cast<const T*>(p.rows) + e * c.S);
+        } else {
+          EnvState s;
+          load_state(p.st, e, s);
+          o = obs_of(s);
+        }
+      }
+      const int sl = it & 1;
+      uint8_t* slot = dyn_smem + L.slots_off + (size_t)(warp * 2 + sl) * L.slot_bytes;
+      if (it >= 2) {
+        mbar_wait(&bars[2 * CW + warp * 2 + sl], (uint32_t)(((it >> 1) - 1) & 1));
+        if (lane == 0) bulk_wait_read_all_but_newest();
+        __syncwarp();
+      }
+      float* ns = reinterpret_cast<float*>(slot + L.ns_off);
+      if (have) {
+        if (p.enc.kind == SUS_ENCODE_GLOBAL) global_ns_rows(c, o, ns + lane * F, 32 * F);
+        else
+          for (int k = 0; k < A; ++k) persp_ns_row(c, o, k, ns + (k * 32 + lane) * F);
+      }
+      write_plane_record(c, o, have, reinterpret_cast<uint16_t*>(slot + L.po_off) + lane * 16);
+      fence_proxy_async_smem();
+      __syncwarp();
+      for (int k = 0; k < A; ++k)
+        drain(p.non_spatial + ((int64_t)k * p.n_items + e0) * F, ns + k * 32 * F, (uint32_t)(cnt * F * 4), lane);
+      __syncwarp();
+      if (lane == 0) {
+        bulk_commit();
+        mbar_arrive(&bars[warp * 2 + sl]);
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+  } else if (warp == CW) {
+    emitter_dispatch(p.enc.kind == SUS_ENCODE_PERSPECTIVE, A, R, p.n_items, p.spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+  }
 }
 
 template <typename T>
@@ -936,6 +1009,12 @@ bool want_ws() {
 unsigned persistent_grid(int64_t n_items, const TileLayout& L, int sms) {
   const int64_t groups = (n_items + 31) / 32;
   const int64_t ctas = (groups + L.warps - 1) / L.warps;
+  return (unsigned)(ctas < sms ? ctas : sms);
+}
+
+unsigned ws_grid(int64_t n_items, const WsLayout& W, int sms) {
+  const int64_t groups = (n_items + 31) / 32;
+  const int64_t ctas = (groups + W.compute_warps - 1) / W.compute_warps;
   return (unsigned)(ctas < sms ? ctas : sms);
 }
 
@@ -1248,6 +1327,12 @@ int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float
   if (e->N == 0) return SUS_OK;
   DeviceInfo di;
   if (int rc = device_info(e->device, di)) return rc;
+  WsLayout W;
+  if (want_ws() && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, W)) {
+    if (int rc = allow_big_smem(k_encode_ws<float, false>, W.total_bytes)) return rc;
+    k_encode_ws<float, false><<<ws_grid(e->N, W, di.sms), (W.compute_warps + 1) * 32, W.total_bytes, (cudaStream_t)stream>>>(p, W);
+    return after_launch("k_encode_ws");
+  }
   TileLayout L;
   if (want_tma() && make_layout(p.c, p.enc, 0, false, di.max_dyn_smem, L)) {
     const size_t smem = (size_t)L.per_warp * L.warps;
@@ -1281,6 +1366,21 @@ int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const 
     return fail(SUS_ERR_INVALID_ARGUMENT, "states dtype must be SUS_F32, SUS_F64 or SUS_I64");
   DeviceInfo di;
   if (int rc = device_info(device, di)) return rc;
+  WsLayout W;
+  if (want_ws() && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, W)) {
+    const unsigned gr = ws_grid(n_items, W, di.sms), threads = (unsigned)(W.compute_warps + 1) * 32;
+    if (dtype == SUS_F32) {
+      if (int rc = allow_big_smem(k_encode_ws<float, true>, W.total_bytes)) return rc;
+      k_encode_ws<float, true><<<gr, threads, W.total_bytes, st>>>(p, W);
+    } else if (dtype == SUS_F64) {
+      if (int rc = allow_big_smem(k_encode_ws<double, true>, W.total_bytes)) return rc;
+      k_encode_ws<double, true><<<gr, threads, W.total_bytes, st>>>(p, W);
+    } else {
+      if (int rc = allow_big_smem(k_encode_ws<long long, true>, W.total_bytes)) return rc;
+      k_encode_ws<long long, true><<<gr, threads, W.total_bytes, st>>>(p, W);
+    }
+    return after_launch("k_encode_ws");
+  }
   TileLayout L;
   if (want_tma() && make_layout(p.c, p.enc, 0, false, di.max_dyn_smem, L)) {
     const size_t smem = (size_t)L.per_warp * L.warps;
