@@ -27,7 +27,8 @@ using namespace susnet;
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kTmaMaxWarps = 12;  // persistent TMA-path CTAs: up to 384 threads, one CTA per SM
+constexpr int kTmaMaxWarps = 16;  // per-warp TMA path (small staging blocks, e.g. Flat rows): up to 512 threads per CTA
+constexpr int kWsMaxWarps = 12;   // warp-specialised path: up to 11 compute warps + the emitter
 constexpr unsigned kFull = 0xffffffffu;
 
 thread_local std::string g_last_error;
@@ -497,7 +498,7 @@ __device__ __forceinline__ void emitter_dispatch(bool persp, int A, int R, int64
 
 // K1+K2, warp-specialised TMA path (susnet_ws.cuh): CW compute warps + one emitter warp per persistent CTA.
 template <int VARIANT>
-__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_ws(const __grid_constant__ StepParams p,
+__global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_step_ws(const __grid_constant__ StepParams p,
                                                                   const __grid_constant__ WsLayout L) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ GridTables tb;
@@ -688,7 +689,7 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_encode_tma(const __gri
 // K2, warp-specialised (see k_step_ws): compute warps unflatten rows / load env state and leave plane records + dense
 // rows; the emitter warp writes the plane tiles.
 template <typename T, bool FROM_ROWS>
-__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_encode_ws(const __grid_constant__ EncodeParams p,
+__global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_encode_ws(const __grid_constant__ EncodeParams p,
                                                                     const __grid_constant__ WsLayout L) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ GridTables tb;
@@ -987,7 +988,7 @@ bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool
   t.slot_bytes = off;
   const int budget = max_dyn_smem - 2048 - 2 * t.tile_bytes - 512;
   int cw = budget / (2 * t.slot_bytes);
-  if (cw > kTmaMaxWarps - 1) cw = kTmaMaxWarps - 1;
+  if (cw > kWsMaxWarps - 1) cw = kWsMaxWarps - 1;
   const char* env_w = std::getenv("SUSNET_WS_WARPS");
   if (env_w && std::atoi(env_w) > 0 && std::atoi(env_w) < cw) cw = std::atoi(env_w);
   if (cw < 2) return false;
