@@ -181,6 +181,13 @@ int sus_env_reset(sus_env_t env, const uint8_t *mask_or_null, void *stream);
  * step is skipped and a device-side error counter is raised (see sus_env_check_actions). */
 int sus_env_step(sus_env_t env, const SusStepIO *io /*host*/, void *stream);
 
+/* n_steps random-policy steps of every env inside ONE launch (state stays in registers): identical to n_steps calls
+ * of sus_env_step with actions == NULL -- same ticks, draws, auto-resets and episode statistics -- but only the final
+ * state is written.  reward_sums: optional [N][A] float64, sum of each agent index's rewards over the rollout.
+ * The inner loop of ReplayBuffer.populate / random-policy evaluation (replay_memory.py:103-143) without a launch
+ * per step. */
+int sus_env_rollout(sus_env_t env, int32_t n_steps, double *reward_sums, void *stream);
+
 /* Synchronises `stream` and returns SUS_ERR_INVALID_ACTION if any step since the last check saw an action
  * index outside its agent's role list (reference: IndexError, base.py:381), else 0. */
 int sus_env_check_actions(sus_env_t env, void *stream);

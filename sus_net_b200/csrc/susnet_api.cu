@@ -318,6 +318,85 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepP
   }
 }
 
+// Random-policy rollout: every env advances `n_steps` steps inside ONE launch with its state in registers
+// (== n_steps calls of step(None): same ticks, same draws, same auto-resets, same episode statistics); only the final
+// state and, optionally, the per-agent reward sums are written.  This is ReplayBuffer.populate's / a random-policy
+// benchmark's inner loop (replay_memory.py:103-143) with no launch per step.
+struct RolloutParams {
+  DevConfig c;
+  StateArrays st;
+  unsigned long long* stats;
+  double* reward_sums;  // [N][A] or nullptr: sum over the rollout of each agent index's rewards
+  uint64_t tick0;
+  int64_t N;
+  int32_t n_steps;
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads) k_rollout(const __grid_constant__ RolloutParams p) {
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const DevConfig& c = p.c;
+  const int A = c.A, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool have = e < p.N;
+  EnvState s = {};
+  if (have) load_state(p.st, e, s);
+  double sums[SUS_MAX_AGENTS];
+#pragma unroll
+  for (int i = 0; i < SUS_MAX_AGENTS; ++i) sums[i] = 0.0;
+  uint32_t acc[SUS_N_STATS];
+#pragma unroll
+  for (int k = 0; k < SUS_N_STATS; ++k) acc[k] = 0;
+  for (int t = 0; t < p.n_steps; ++t) {
+    const uint64_t tick = p.tick0 + (uint64_t)t;
+    if (have) {
+      uint64_t acts = 0;
+      WordStream wa;
+      wa.init(c, nullptr, (uint32_t)e, tick, P_ACT_FUSED);
+      for (int i = 0; i < A; ++i)
+        acts |= (uint64_t)bounded(wa.word(i), n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) << (8 * i);
+      WordStream ws;
+      ws.init(c, nullptr, (uint32_t)e, tick, P_STEP);
+      StepResult r = {};
+      step_env<VARIANT>(c, tb, s, acts, ws, r);
+      if (p.reward_sums) {
+#pragma unroll
+        for (int i = 0; i < SUS_MAX_AGENTS; ++i)
+          if (i < A) sums[i] += agent_reward<VARIANT>(c, s, r, i);
+      }
+      if (r.done || r.trunc) {  // per-thread accumulation; flushed once at the end of the rollout
+        acc[SUS_S_EPISODES] += 1u; acc[SUS_S_CREW_WON] += (s.misc >> 24) & 1u; acc[SUS_S_IMPOSTER_WON] += (s.misc >> 25) & 1u;
+        acc[SUS_S_IMP_KILLED_CREW] += s.misc & 0xff; acc[SUS_S_COMPLETED_JOBS] += s.completed;
+        acc[SUS_S_SABOTAGED_JOBS] += s.sabotaged; acc[SUS_S_IMP_VOTED_OUT] += (s.misc >> 8) & 0xff;
+        acc[SUS_S_CREW_VOTED_OUT] += (s.misc >> 16) & 0xff; acc[SUS_S_TOTAL_TIME_STEPS] += s.nsteps;
+        acc[SUS_S_TRUNCATED] += r.trunc ? 1u : 0u;
+        if (c.auto_reset) {
+          WordStream wr;
+          wr.init(c, nullptr, (uint32_t)e, tick, P_AUTORESET);
+          reset_env(c, tb, s, wr);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < SUS_N_STATS; ++k) {
+    const unsigned long long sum = (unsigned long long)__reduce_add_sync(kFull, acc[k] & 0xffffu) +
+                                   ((unsigned long long)__reduce_add_sync(kFull, acc[k] >> 16) << 16);
+    if (lane == 0 && sum) atomicAdd(p.stats + k, sum);
+  }
+  if (have) {
+    store_state(p.st, e, s, true);
+    if (p.reward_sums)
+      for (int i = 0; i < A; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < SUS_MAX_AGENTS; ++q) v = q == i ? sums[q] : v;
+        p.reward_sums[e * A + i] = v;
+      }
+  }
+}
+
 // K1 (+K2), TMA path: persistent CTAs (one per SM), each warp walks groups of 32 envs; rewards, the replay-layout
 // state row and the feature tensors are staged in shared memory and leave the SM as TMA bulk stores.
 template <int VARIANT, bool ENCODE>
@@ -1234,6 +1313,26 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   }
 #undef SUS_LAUNCH_STEP
   return after_launch("k_step");
+}
+
+int sus_env_rollout(sus_env_t e, int32_t n_steps, double* reward_sums, void* stream) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (n_steps < 0) return fail(SUS_ERR_INVALID_ARGUMENT, "n_steps < 0");
+  if (e->inj_step || e->inj_reset || e->inj_act) return fail(SUS_ERR_INVALID_ARGUMENT, "rollout does not take injected words");
+  DeviceGuard g(e->device);
+  RolloutParams p;
+  p.c = e->dc; p.st = e->st; p.stats = e->stats; p.reward_sums = reward_sums; p.tick0 = e->step_tick; p.N = e->N;
+  p.n_steps = n_steps;
+  e->step_tick += (uint64_t)n_steps;
+  if (e->N == 0 || n_steps == 0) return SUS_OK;
+  const unsigned gr = grid_for(e->N);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (e->cfg.variant) {
+    case SUS_VARIANT_BASE: k_rollout<SUS_VARIANT_BASE><<<gr, kThreads, 0, st>>>(p); break;
+    case SUS_VARIANT_TAGGING: k_rollout<SUS_VARIANT_TAGGING><<<gr, kThreads, 0, st>>>(p); break;
+    default: k_rollout<SUS_VARIANT_TRAINING_GROUND><<<gr, kThreads, 0, st>>>(p); break;
+  }
+  return after_launch("k_rollout");
 }
 
 int sus_env_check_actions(sus_env_t e, void* stream) {

@@ -469,6 +469,16 @@ class BatchedFourRoomEnv:
     def _full_state_tuple(self):
         return self._state_tuple()
 
+    def rollout(self, n_steps, reward_sums=False):
+        """`n_steps` random-policy steps of every env in ONE kernel launch (batched mode): the same trajectory, draws,
+        auto-resets and episode statistics as `n_steps` calls of `step(None)`, without any per-step output.  Returns
+        the (N, A) float64 per-agent reward sums if `reward_sums` else None."""
+        if not self._was_reset:
+            raise AssertionError("reset() must be called before rollout()")
+        out = torch.zeros((self.num_envs, self.n_agents), dtype=torch.float64, device=self.device) if reward_sums else None
+        L.check(self.lib.sus_env_rollout(self._h, int(n_steps), _ptr(out), self._stream()))
+        return out
+
     def check_actions(self):
         """Raise IndexError if any step since the last check saw an index outside an agent's role list."""
         L.check(self.lib.sus_env_check_actions(self._h, self._stream()))

@@ -364,3 +364,27 @@ def test_random_constructor_arguments_match_oracle(cuda_lib, k):
         else:
             sp, ns = oracle.encode_global(cfg, cur)
             assert all(np.array_equal(cpu(v[0])[:, 0], sp) and np.array_equal(cpu(v[1])[:, 0], ns[i]) for i, v in enumerate(views))
+
+
+@pytest.mark.parametrize("name", ["cfg2_itg_1v1_wall", "cfg3_tagging_1v2", "cfg4_base_1v4", "base_2v3_j3"])
+def test_rollout_kernel_equals_repeated_steps(cuda_lib, name):
+    """rollout(T) == T x step(None): final states, per-episode counters, episode statistics, reward sums."""
+    cfg = CASES[name]
+    N, T = 1500, 137
+    a = make_cuda_env(cfg, N, seed=3, env_id_base=9)
+    b = make_cuda_env(cfg, N, seed=3, env_id_base=9)
+    orc = oracle.OracleEnv(cfg, N, seed=3, env_id_base=9)
+    a.reset(); b.reset(); orc.reset()
+    b._rewards = torch.zeros((N, b.n_agents), dtype=torch.float64, device=b.device)
+    sums = a.rollout(T, reward_sums=True)
+    want = torch.zeros_like(sums)
+    for _ in range(T):
+        want += b.step(None)[1]
+        orc.step(None)
+    assert torch.equal(a.flat_states(torch.int64), b.flat_states(torch.int64))
+    assert np.array_equal(cpu(a.flat_states(torch.int64)), orc.flat_states())
+    assert torch.equal(a.metrics_batch(), b.metrics_batch()) and torch.equal(a.episode_stats(), b.episode_stats())
+    assert np.array_equal(cpu(a.episode_stats()), orc.stats())
+    assert torch.equal(sums, want)  # same float64 additions in the same order
+    a.rollout(5); [b.step(None) for _ in range(5)]  # ticks stay aligned afterwards
+    assert torch.equal(a.flat_states(torch.int64), b.flat_states(torch.int64))
