@@ -388,3 +388,38 @@ def test_rollout_kernel_equals_repeated_steps(cuda_lib, name):
     assert torch.equal(sums, want)  # same float64 additions in the same order
     a.rollout(5); [b.step(None) for _ in range(5)]  # ticks stay aligned afterwards
     assert torch.equal(a.flat_states(torch.int64), b.flat_states(torch.int64))
+
+
+def test_unaligned_output_pointers_through_the_c_abi(cuda_lib):
+    """Feature tensors that are only 4-byte aligned (sliced views): the TMA paths must fall back to ordinary stores for
+    every block whose address or size is not a 16-byte multiple, with identical results."""
+    import ctypes as C
+
+    import sus_net_b200 as S
+    from sus_net_b200 import _lib as L
+
+    cfg = CASES["cfg4_base_1v4"]
+    for N in (1003, 64):
+        env = make_cuda_env(cfg, N, seed=2)
+        env.reset()
+        for _ in range(3):
+            env.step(None)
+        cur = cpu(env.flat_states(torch.int64))
+        for kind, enc in ((L.ENCODE_GLOBAL, oracle.encode_global), (L.ENCODE_PERSPECTIVE, oracle.encode_perspective)):
+            sh = L.SusEncodeShape()
+            spec = L.SusEncodeSpec(kind=kind)
+            L.check(env.lib.sus_encode_shape(C.byref(env._cfg), C.byref(spec), C.byref(sh)))
+            sp_n = sh.spatial_views * N * sh.spatial_floats
+            ns_n = sh.non_spatial_views * N * sh.non_spatial_floats
+            for off in (1, 2, 3):  # floats: 4, 8, 12 bytes past a 16-byte boundary
+                sp_raw = torch.full((sp_n + 8,), -7.0, device=env.device)
+                ns_raw = torch.full((ns_n + 8,), -7.0, device=env.device)
+                sp, ns = sp_raw[off:off + sp_n], ns_raw[off:off + ns_n]
+                L.check(env.lib.sus_env_encode(env._h, C.byref(spec), C.c_void_p(sp.data_ptr()), C.c_void_p(ns.data_ptr()),
+                                               env._stream()))
+                want_sp, want_ns = enc(cfg, cur)
+                assert np.array_equal(cpu(sp).reshape(want_sp.shape), want_sp)
+                assert np.array_equal(cpu(ns).reshape(want_ns.shape), want_ns)
+                # nothing outside the tensors was touched
+                assert (cpu(sp_raw[:off]) == -7).all() and (cpu(sp_raw[off + sp_n:]) == -7).all()
+                assert (cpu(ns_raw[:off]) == -7).all() and (cpu(ns_raw[off + ns_n:]) == -7).all()

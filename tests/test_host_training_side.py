@@ -1,0 +1,95 @@
+"""CPU: host-side pieces of the "next" rows that need no GPU -- schedule, replay-buffer add/sample semantics on a CPU
+device (same code path as on the GPU apart from the push kernel), metrics adaptor."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def S():
+    from sus_net_b200 import build as B
+
+    B.build()
+    import sus_net_b200
+
+    return sus_net_b200
+
+
+def test_exponential_schedule_matches_reference_formula(S):
+    sch = S.ExponentialSchedule(1.0, 0.05, 1_000_000)  # report p.5: eps 1 -> 0.05 over 1M steps
+    assert sch.value(0) == 1.0 and sch.value(-3) == 1.0 and sch.value(1_000_000) == 0.05 and sch.value(2_000_000) == 0.05
+    b = math.log(0.05) / 999_999
+    for t in (1, 10, 999, 500_000, 999_999):
+        assert sch.value(t) == pytest.approx(math.exp(b * t), rel=1e-12)
+    from oracle import ref_harness as H
+
+    if H.reference_available():
+        H.import_reference()
+        from src.scheduler import ExponentialSchedule as Ref
+
+        ref = Ref(1.0, 0.05, 1_000_000)
+        for t in (0, 1, 17, 123456, 999_999, 1_000_000):
+            assert float(ref.value(t)) == pytest.approx(sch.value(t), rel=1e-12)
+
+
+def test_replay_buffer_add_sample_on_cpu_matches_reference_layout(S):
+    buf = S.ReplayBuffer(max_size=5, state_size=6, trajectory_size=2, n_agents=2, n_imposters=1, device="cpu")
+    assert buf.states.shape == (5, 2, 6) and buf.states.dtype == torch.float32
+    assert buf.actions.shape == (5, 2) and buf.actions.dtype == torch.int64
+    assert buf.rewards.shape == (5, 2) and buf.next_states.shape == (5, 2, 6)
+    assert buf.dones.shape == (5, 1) and buf.dones.dtype == torch.bool
+    assert buf.imposters.shape == (5, 1) and buf.imposters.dtype == torch.int16
+    for k in range(7):  # wraps after 5 (replay_memory.py:70-72)
+        st = np.full((2, 6), k, dtype=np.float64)
+        buf.add(state=st, action=np.array([k, k + 1]), reward=np.array([0.5 * k, -k]), next_state=st + 1, done=k % 2 == 1,
+                imposters=np.array([k % 2]))
+    assert buf.idx == 2 and buf.size == 5
+    assert buf.states[0, 0, 0] == 5 and buf.states[1, 0, 0] == 6 and buf.states[2, 0, 0] == 2
+    assert buf.actions[1].tolist() == [6, 7] and buf.rewards[1].tolist() == [3.0, -6.0] and bool(buf.dones[1, 0]) is False
+    assert bool(buf.dones[0, 0]) is True and buf.imposters[0, 0] == 1
+    g = torch.Generator().manual_seed(0)
+    b = buf.sample(64, generator=g)
+    assert b._fields == ("states", "actions", "rewards", "next_states", "imposters", "dones")
+    assert b.states.shape == (64, 2, 6) and b.dones.shape == (64, 1)
+    assert torch.equal(b.next_states, b.states + 1)  # rows stay aligned across the six tensors
+    with pytest.raises(AssertionError):
+        S.ReplayBuffer(5, 6, 2, 2, 1, device="cpu").sample(1)  # empty (replay_memory.py:83)
+    for bad in (dict(max_size=0), dict(trajectory_size=0), dict(state_size=0), dict(n_agents=0)):
+        kw = dict(max_size=5, state_size=6, trajectory_size=2, n_agents=2, n_imposters=1)
+        kw.update(bad)
+        with pytest.raises(AssertionError):
+            S.ReplayBuffer(device="cpu", **kw)
+    from oracle import ref_harness as H
+
+    if H.reference_available():  # identical tensors to the reference's own buffer fed the same transitions
+        H.import_reference()
+        from src.replay_memory import ReplayBuffer as Ref
+
+        ref = Ref(max_size=5, state_size=6, trajectory_size=2, n_agents=2, n_imposters=1)
+        mine = S.ReplayBuffer(max_size=5, state_size=6, trajectory_size=2, n_agents=2, n_imposters=1, device="cpu")
+        rng = np.random.default_rng(0)
+        for k in range(9):
+            st, nx = rng.integers(0, 9, (2, 6)).astype(np.float64), rng.integers(0, 9, (2, 6)).astype(np.float64)
+            a, r = rng.integers(0, 6, 2), rng.normal(size=2)
+            for bfr in (ref, mine):
+                bfr.add(st, a, r, nx, bool(k % 3 == 0), np.array([k % 2]))
+        for name in ("states", "actions", "rewards", "next_states", "dones", "imposters"):
+            assert torch.equal(getattr(ref, name), getattr(mine, name)), name
+        assert (ref.idx, ref.size) == (mine.idx, mine.size)
+
+
+def test_episodic_metric_handler_from_stats(S, tmp_path):
+    m = S.EpisodicMetricHandler()
+    m.update_from_stats(torch.tensor([10, 6, 4, 20, 30, 2, 1, 0, 900, 1]))
+    avg = m.compute()
+    assert avg[S.SusMetrics.CREW_WON] == 0.6 and avg[S.SusMetrics.IMPOSTER_WON] == 0.4
+    assert avg[S.SusMetrics.TOTAL_TIME_STEPS] == 90.0 and avg[S.SusMetrics.IMP_KILLED_CREW] == 2.0
+    assert set(avg) == set(S.SusMetrics) and len(avg) == 13
+    p = tmp_path / "metrics.json"
+    m.save_metrics(p)
+    import json
+
+    d = json.loads(p.read_text())
+    assert d["episodes"] == 10 and d["truncated_episodes"] == 1 and d["totals"]["completed_jobs"] == 30
