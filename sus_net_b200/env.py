@@ -159,7 +159,18 @@ class BatchedFourRoomEnv:
         self._done = torch.zeros(N, dtype=torch.bool, device=dev)  # the kernel writes 0/1 bytes
         self._trunc = torch.zeros(N, dtype=torch.bool, device=dev)
         self._next_flat = torch.zeros((N, S), dtype=torch.float32, device=dev)
-        self._metrics_buf = torch.zeros((N, L.N_METRICS), dtype=torch.int64, device=dev) if not self.batched else None
+        self._metrics_buf = None
+        if not self.batched:
+            # reference mode: every per-step output lives in ONE device buffer so a step costs one launch + one D2H copy
+            nb_r, nb_m, nb_f = 8 * A, 8 * L.N_METRICS, 4 * S
+            self._ref_dev = torch.zeros(nb_r + nb_m + ((nb_f + 7) // 8) * 8 + 8, dtype=torch.uint8, device=dev)
+            self._ref_host = torch.zeros_like(self._ref_dev, device="cpu").pin_memory()
+            self._rewards = self._ref_dev[:nb_r].view(torch.float64).view(1, A)
+            self._metrics_buf = self._ref_dev[nb_r:nb_r + nb_m].view(torch.int64).view(1, L.N_METRICS)
+            self._next_flat = self._ref_dev[nb_r + nb_m:nb_r + nb_m + nb_f].view(torch.float32).view(1, S)
+            flags = self._ref_dev[nb_r + nb_m + ((nb_f + 7) // 8) * 8:]
+            self._done, self._trunc = flags[0:1].view(torch.bool), flags[1:2].view(torch.bool)
+            self._ref_layout = (nb_r, nb_m, nb_f)
         self.emit_next_states = True  # batched mode: write the (N, S) replay-layout next-state rows every step
         self.emit_imposters = False   # batched mode: also write the (N, n_imposters) int16 replay column
         self._imposters_buf = None
@@ -368,7 +379,13 @@ class BatchedFourRoomEnv:
         return self.metrics.get_metrics()
 
     def _sync_host(self):
-        flat = self.flat_states(dtype=torch.int64)[0].cpu().numpy()
+        self._set_host_state(self.flat_states(dtype=torch.int64)[0].cpu().numpy())
+        self._imp_cache = self.imposter_mask_batch[0].cpu().numpy()
+        mt = self.metrics_batch()[0].cpu().numpy()
+        self._host_metrics = mt
+        self.t = int(min(mt[0], self.max_time_steps - 1))
+
+    def _set_host_state(self, flat):
         hs = {}
         for name, a, b, shape, dt in self._field_slices():
             arr = np.asarray(flat[a:b]).reshape(shape)
@@ -377,10 +394,6 @@ class BatchedFourRoomEnv:
             hs["job_positions"] = np.zeros((0, 2), dtype=np.int64)
             hs["completed_jobs"] = np.zeros((0,), dtype=bool)
         self._host_state = hs
-        self._imp_cache = self.imposter_mask_batch[0].cpu().numpy()
-        mt = self.metrics_batch()[0].cpu().numpy()
-        self._host_metrics = mt
-        self.t = int(min(mt[0], self.max_time_steps - 1))
 
     def _state_tuple(self):
         hs = self._host_state
@@ -427,6 +440,11 @@ class BatchedFourRoomEnv:
             if not self.batched:
                 assert len(agent_actions) == A, f"Expected {A} actions, got {len(agent_actions)}"  # base.py:357-359
                 assert all(a < self.action_space.n for a in agent_actions), f"Invalid action(s) {agent_actions}"
+                n_tag = A - 1 if self._VARIANT == L.VARIANT_TAGGING else 0
+                for i, a in enumerate(agent_actions):  # agent_action_map[i][a] (base.py:381): IndexError past the list
+                    n_role = (len(self.imposter_actions) if self._imp_cache[i] else len(self.crew_actions)) + n_tag
+                    if not 0 <= int(a) < n_role:
+                        raise IndexError("list index out of range")
                 agent_actions = np.asarray(agent_actions).reshape(1, A)
             if isinstance(agent_actions, torch.Tensor) and agent_actions.device == self.device and \
                     agent_actions.dtype in (torch.uint8, torch.int32, torch.int64) and agent_actions.is_contiguous():
@@ -457,14 +475,22 @@ class BatchedFourRoomEnv:
             io.spatial = featurizer._sp_buf.data_ptr() if featurizer._sp_buf is not None else None
             io.non_spatial = featurizer._ns_buf.data_ptr()
         L.check(self.lib.sus_env_step(self._h, C.byref(io), self._stream()))
-        if check if check is not None else not self.batched:
+        if check if check is not None else False:
             L.check(self.lib.sus_env_check_actions(self._h, self._stream()))
         if self.batched:
             return (self._next_flat if self.emit_next_states else None), rewards, done, trunc, {}
-        self._sync_host()
-        rewards = self._rewards[0].cpu().numpy().copy()
-        return (self._full_state_tuple(), rewards, bool(self._done[0].item()), bool(self._trunc[0].item()),
-                self.metrics.get_metrics())
+        # reference mode: one D2H copy of the packed outputs, then numpy views
+        self._ref_host.copy_(self._ref_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        nb_r, nb_m, nb_f = self._ref_layout
+        h = self._ref_host.numpy()
+        rewards = h[:nb_r].view(np.float64).copy()
+        self._host_metrics = h[nb_r:nb_r + nb_m].view(np.int64).copy()
+        flat = h[nb_r + nb_m:nb_r + nb_m + nb_f].view(np.float32).astype(np.int64)
+        flags = h[nb_r + nb_m + ((nb_f + 7) // 8) * 8:]
+        self._set_host_state(flat)
+        self.t = int(min(self._host_metrics[0], self.max_time_steps - 1))
+        return (self._full_state_tuple(), rewards, bool(flags[0]), bool(flags[1]), self.metrics.get_metrics())
 
     def _full_state_tuple(self):
         return self._state_tuple()
