@@ -168,3 +168,14 @@ def test_two_rank_gloo_stat_reduce_matches_single_shard():
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_missing_cuda_library_is_an_import_error(lib, monkeypatch, tmp_path):
+    """No silent fallback: without the built .so the binding raises (the product never routes through the oracle)."""
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", str(tmp_path / "libsusnet_b200.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        lib.lib()
+    src = "".join(open(os.path.join(ROOT, "sus_net_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "sus_net_b200"))
+                  if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src
