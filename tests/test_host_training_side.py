@@ -93,3 +93,38 @@ def test_episodic_metric_handler_from_stats(S, tmp_path):
 
     d = json.loads(p.read_text())
     assert d["episodes"] == 10 and d["truncated_episodes"] == 1 and d["totals"]["completed_jobs"] == 30
+
+
+_GRAD_WORKER = r'''
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sus_net_b200.train import allreduce_grads
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+torch.manual_seed(0)
+m = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.PReLU(), torch.nn.Linear(3, 2))
+x = torch.full((5, 4), float(rank + 1))
+m(x).sum().backward()
+local = [p.grad.clone() for p in m.parameters()]
+allreduce_grads(m)
+# the other rank's gradients, recomputed locally
+m2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.PReLU(), torch.nn.Linear(3, 2))
+m2.load_state_dict(m.state_dict())
+m2(torch.full((5, 4), float(2 - rank))).sum().backward()
+for p, g1, p2 in zip(m.parameters(), local, m2.parameters()):
+    assert torch.allclose(p.grad, (g1 + p2.grad) / 2, atol=1e-6)
+dist.destroy_process_group()
+'''
+
+
+def test_gradient_allreduce_two_ranks_gloo(S):
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = str(31000 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, "-c", _GRAD_WORKER, root, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
