@@ -33,10 +33,15 @@ class ExponentialSchedule:
 
 class BatchedActor:
     """train.py:351-381 for every env at once: per agent view, alive imposters act with `imposter_model`, alive crew
-    with `crew_model`, each ε-greedy over its role's action count; dead agents keep action 0."""
+    with `crew_model`, each ε-greedy over its role's action count; dead agents keep action 0.
 
-    def __init__(self, env, imposter_model, crew_model, generator=None):
-        self.env, self.imposter_model, self.crew_model, self.generator = env, imposter_model, crew_model, generator
+    dense=True (default) evaluates both networks on all N rows of a view and selects per row with `torch.where` --
+    no host synchronisation, which is what matters at 10^5..10^6 envs; dense=False gathers the rows of each role first
+    (fewer network rows, one `nonzero` sync per role and view), like the reference evaluates one row per agent."""
+
+    def __init__(self, env, imposter_model, crew_model, generator=None, dense=True):
+        self.env, self.imposter_model, self.crew_model = env, imposter_model, crew_model
+        self.generator, self.dense = generator, dense
 
     @torch.no_grad()
     def act(self, views, eps, flat_states, imposter_mask=None):
@@ -47,15 +52,25 @@ class BatchedActor:
         alive = flat_states[:, 2 * A:3 * A] != 0
         imp = env.imposter_mask_batch if imposter_mask is None else imposter_mask
         actions = torch.zeros((N, A), dtype=torch.int32, device=dev)
+        roles = ((self.imposter_model, env.n_imposter_actions), (self.crew_model, env.n_crew_actions))
         for k, (spatial, non_spatial) in enumerate(views):
-            for mask, model, n_act in ((imp[:, k] & alive[:, k], self.imposter_model, env.n_imposter_actions),
-                                       (~imp[:, k] & alive[:, k], self.crew_model, env.n_crew_actions)):
+            if self.dense:
+                picks = []
+                for model, n_act in roles:
+                    explore = torch.rand(N, device=dev, generator=self.generator) <= eps  # train.py:363,374
+                    rand_a = torch.randint(0, n_act, (N,), device=dev, generator=self.generator)
+                    greedy = torch.argmax(model(spatial, non_spatial), dim=1)  # train.py:368-370,379-381
+                    picks.append(torch.where(explore, rand_a, greedy))
+                a = torch.where(imp[:, k], picks[0], picks[1])
+                actions[:, k] = torch.where(alive[:, k], a, torch.zeros_like(a)).to(torch.int32)
+                continue
+            for mask, (model, n_act) in zip((imp[:, k] & alive[:, k], ~imp[:, k] & alive[:, k]), roles):
                 idx = mask.nonzero(as_tuple=True)[0]
                 if idx.numel() == 0:
                     continue
-                explore = torch.rand(idx.numel(), device=dev, generator=self.generator) <= eps  # train.py:363,374
+                explore = torch.rand(idx.numel(), device=dev, generator=self.generator) <= eps
                 rand_a = torch.randint(0, n_act, (idx.numel(),), device=dev, generator=self.generator)
-                greedy = torch.argmax(model(spatial[idx], non_spatial[idx]), dim=1)  # train.py:368-370,379-381
+                greedy = torch.argmax(model(spatial[idx], non_spatial[idx]), dim=1)
                 actions[idx, k] = torch.where(explore, rand_a, greedy).to(torch.int32)
         return actions
 
