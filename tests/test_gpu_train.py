@@ -87,7 +87,7 @@ def test_batched_training_loop_runs_and_acts_within_role_ranges(cuda_lib):
     feat.fit(seq)
     views = feat.generate_featurized_states()
     acts = S.BatchedActor(env, imp, crew).act(views, 0.0, seq[:, -1])
-    assert torch.equal(acts, S.BatchedActor(env, imp, crew, dense=False).act(views, 0.0, seq[:, -1]))  # greedy: both modes agree
+    assert torch.equal(acts, S.BatchedActor(env, imp, crew, dense=True).act(views, 0.0, seq[:, -1]))  # greedy: both modes agree
     alive = seq[:, -1, 10:15] != 0
     mask = env.imposter_mask_batch
     assert (acts[~alive] == 0).all() and (acts[mask].max() <= 5) and (acts[~mask].max() <= 4)
