@@ -1,14 +1,20 @@
 // susnet_api.cu -- kernels and C ABI (include/susnet_b200.h) of the B200-native Sus-Net simulator.
 //
-// Kernels (all sm_100a, one thread per env / item, 256-thread CTAs, wall grid staged in shared memory):
-//   K0 k_reset           FourRoomEnv.reset for a masked subset of envs
-//   K1 k_step<V, ENC>    fused step: action decode, ordered per-agent loop (move with wall collision, kill,
-//                        fix, sabotage, tag), vote tally, win / reward / done / truncation, episode-stat
-//                        flush, auto-reset, and (ENC) the observation encode of the state the next action
-//                        is taken from
-//   K2 k_encode_env / k_encode_rows<T>   featurizers on live env state / on (B*T, S) flattened rows
-//   K3 k_sample_actions  role-aware uniform random actions
-//   plus small export / import kernels for the reference's flatten order.
+// Kernels (all sm_100a; one thread owns one env / item; the wall grid is staged in shared memory):
+//   K0    k_reset              FourRoomEnv.reset for a masked subset of envs
+//   K1    k_step<V, false>     the step: action decode, ordered per-agent loop (move with wall collision, kill, fix,
+//                              sabotage, tag), vote tally, win / reward / done / truncation, episode-stat flush,
+//                              auto-reset.  One thread per env, 256-thread CTAs (step-only launches).
+//   K1+K2 k_step_ws<V>         the step FUSED with the observation encode of the state the next action is taken
+//                              from, warp-specialised: compute warps + one TMA emitter warp per persistent CTA
+//                              (Global / Perspective; the headline kernel)
+//         k_step_tma<V, true>  same fusion, every warp stages and bulk-stores its own tiles (Flat encodes)
+//         k_step<V, true>      same fusion with direct register stores (fallback, SUSNET_PATH=direct)
+//   K2    k_encode_ws / k_encode_tma / k_encode_env / k_encode_rows<T>
+//                              featurizers on live env state / on (B*T, S) flattened rows (= featurizer.fit)
+//   K3    k_sample_actions     role-aware uniform random actions
+//         k_rollout<V>         n random-policy steps per launch with the env state in registers
+//   plus small export / import kernels for the reference's flatten order (and k_replay_push in susnet_replay.cu).
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
