@@ -221,6 +221,14 @@ int sus_encode_from_flat(const SusConfig *cfg /*host*/, const SusEncodeSpec *spe
 int sus_env_stats(sus_env_t env, int64_t *out, void *stream);
 int sus_env_clear_stats(sus_env_t env, void *stream);
 
+/* Per-agent running returns exactly as train() keeps them: G = reward + gamma * G after every step (train.py:386),
+ * G[imposter_mask].mean() and G[~imposter_mask].mean() summed over finished episodes (train.py:421-424), G = 0 at
+ * every episode start (train.py:324,436).  Together with sus_env_stats these are the 12 entries of the episode-stat
+ * vector that the multi-GPU driver all-reduces.  Tracking costs 16 * A bytes of state traffic per env-step. */
+int sus_env_track_returns(sus_env_t env, double gamma, void *stream);
+/* out: float64[2] = {sum of imposter returns, sum of crew returns} over the episodes counted in SUS_S_EPISODES. */
+int sus_env_return_sums(sus_env_t env, double *out, void *stream);
+
 /* Launch ticks of the three Philox streams (host values), for checkpoint/resume. */
 int sus_env_get_ticks(sus_env_t env, uint64_t *step_tick, uint64_t *reset_epoch, uint64_t *act_epoch /*host*/);
 int sus_env_set_ticks(sus_env_t env, uint64_t step_tick, uint64_t reset_epoch, uint64_t act_epoch);

@@ -89,6 +89,9 @@ def lib():
         L.orc_flat_feature_size.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_int]
         L.orc_encode_flat.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_track_returns.argtypes = [C.c_void_p, C.c_double]
+        L.orc_return_sums.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_export_returns.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -159,6 +162,19 @@ class OracleEnv:
     def stats(self):
         out = np.zeros(N_STATS, dtype=np.int64)
         lib().orc_stats(self._h, _p(out))
+        return out
+
+    def track_returns(self, gamma):
+        lib().orc_track_returns(self._h, float(gamma))
+
+    def return_sums(self):
+        out = np.zeros(2, dtype=np.float64)
+        lib().orc_return_sums(self._h, _p(out))
+        return out
+
+    def returns(self):
+        out = np.zeros((self.N, self.A), dtype=np.float64)
+        lib().orc_export_returns(self._h, _p(out))
         return out
 
     def sample_actions(self, out=None):

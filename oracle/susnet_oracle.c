@@ -67,6 +67,7 @@ typedef struct {
   int32_t tag_timer;
   int32_t t;
   int64_t metrics[ORC_N_METRICS];
+  double G[ORC_MAX_AGENTS]; /* running returns as train() keeps them (train.py:324,386,436) */
 } orc_env;
 
 typedef struct {
@@ -80,6 +81,8 @@ typedef struct {
   int32_t valid_xy[81][2]; /* row-major argwhere(grid): base.py:199 */
   orc_env *envs;
   int64_t stats[ORC_N_STATS];
+  int32_t track_returns;
+  double gamma, ret_sums[2]; /* sums of G[imposter_mask].mean() / G[~imposter_mask].mean() at episode ends */
   const uint32_t *inj_step, *inj_reset, *inj_act; /* injected raw words for the next launch */
 } orc_handle;
 
@@ -475,6 +478,19 @@ int orc_step(orc_handle *h, const int32_t *actions, int32_t *actions_out, double
       done[e] = d; trunc[e] = t;
       if (next_flat) env_flatten(h, s, next_flat + (size_t)e * h->S);
       if (metrics_out) memcpy(metrics_out + (size_t)e * ORC_N_METRICS, s->metrics, sizeof(s->metrics));
+      if (h->track_returns) { /* train.py:386: G = reward + gamma * G */
+        double gi = 0, gc = 0;
+        int ni = 0, nc = 0;
+        for (int i = 0; i < A; ++i) {
+          s->G[i] = rew[i] + h->gamma * s->G[i];
+          if (s->imposter[i]) { gi += s->G[i]; ni++; } else { gc += s->G[i]; nc++; }
+        }
+        if (d || t) { /* train.py:421-424,436 */
+#pragma omp critical
+          { h->ret_sums[0] += gi / ni; h->ret_sums[1] += gc / nc; }
+          for (int i = 0; i < A; ++i) s->G[i] = 0;
+        }
+      }
       if (d || t) {
         loc[0] += 1; loc[1] += s->metrics[M_CREW_WON]; loc[2] += s->metrics[M_IMP_WON];
         loc[3] += s->metrics[M_KILLS]; loc[4] += s->metrics[M_COMPLETED]; loc[5] += s->metrics[M_SABOTAGED];
@@ -504,6 +520,17 @@ int orc_export_metrics(const orc_handle *h, int64_t *out) {
 
 int orc_imposter_mask(const orc_handle *h, uint8_t *out) {
   for (int e = 0; e < h->N; ++e) memcpy(out + (size_t)e * h->A, h->envs[e].imposter, (size_t)h->A);
+  return 0;
+}
+
+int orc_track_returns(orc_handle *h, double gamma) {
+  h->track_returns = 1; h->gamma = gamma; h->ret_sums[0] = h->ret_sums[1] = 0;
+  for (int e = 0; e < h->N; ++e) memset(h->envs[e].G, 0, sizeof(h->envs[e].G));
+  return 0;
+}
+int orc_return_sums(const orc_handle *h, double *out) { out[0] = h->ret_sums[0]; out[1] = h->ret_sums[1]; return 0; }
+int orc_export_returns(const orc_handle *h, double *out) { /* [N][A] */
+  for (int e = 0; e < h->N; ++e) memcpy(out + (size_t)e * h->A, h->envs[e].G, sizeof(double) * (size_t)h->A);
   return 0;
 }
 

@@ -30,7 +30,7 @@ from .featurizers import (  # noqa: F401
     WallsFeaturizer,
 )
 from .metrics import METRIC_ORDER, STAT_KEYS, EpisodicMetricHandler, SusMetrics  # noqa: F401
-from .distributed import reduce_episode_stats, shard_range  # noqa: F401
+from .distributed import reduce_episode_stats, reduce_return_sums, shard_range  # noqa: F401
 from .host_pipeline import HostStepper  # noqa: F401
 from .replay_memory import Batch, ReplayBuffer  # noqa: F401
 from .train import BatchedActor, DQNTeamTrainer, ExponentialSchedule, allreduce_grads, train_batched  # noqa: F401

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "sus_env_sample_actions", "sus_env_export_flat", "sus_env_import_flat", "sus_env_export_imposter_mask",
     "sus_env_export_metrics", "sus_env_encode", "sus_encode_from_flat", "sus_env_stats", "sus_env_clear_stats",
     "sus_env_get_ticks", "sus_env_set_ticks", "sus_env_state_arrays", "sus_env_debug_inject_words",
-    "sus_launch_count", "sus_replay_push", "sus_env_rollout",
+    "sus_launch_count", "sus_replay_push", "sus_env_rollout", "sus_env_track_returns", "sus_env_return_sums",
 )
 
 
@@ -96,6 +96,8 @@ def lib():
         "sus_env_step": ([vp, C.POINTER(SusStepIO), vp], C.c_int),
         "sus_env_check_actions": ([vp, vp], C.c_int),
         "sus_env_rollout": ([vp, i32, vp, vp], C.c_int),
+        "sus_env_track_returns": ([vp, C.c_double, vp], C.c_int),
+        "sus_env_return_sums": ([vp, vp, vp], C.c_int),
         "sus_env_sample_actions": ([vp, vp, vp], C.c_int),
         "sus_env_export_flat": ([vp, i32, vp, vp], C.c_int),
         "sus_env_import_flat": ([vp, vp, vp, vp, vp], C.c_int),

@@ -82,6 +82,9 @@ struct StepParams {
   const uint32_t* inj_act;
   unsigned long long* stats;
   uint32_t* err;
+  double* ret;       // [A][N] running return G of every agent (train.py:324,386), or nullptr when not tracked
+  double* ret_sums;  // [2] sums over finished episodes of mean imposter / mean crew return (train.py:421-424)
+  double gamma;
   uint64_t tick;
   int64_t N;
   int32_t actions_dtype, rewards_dtype;
@@ -242,13 +245,24 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
   step_env<VARIANT>(c, tb, s, acts, ws, r);
   stepped = true;
   finished = r.done || r.trunc;
-  if (rew_row) {
-    if (p.rewards_dtype == SUS_F64) {
-      double* o = static_cast<double*>(rew_row);
-      for (int i = 0; i < A; ++i) o[i] = agent_reward<VARIANT>(c, s, r, i);
-    } else {
-      float* o = static_cast<float*>(rew_row);
-      for (int i = 0; i < A; ++i) o[i] = (float)agent_reward<VARIANT>(c, s, r, i);
+  r.ret_imp = r.ret_crew = 0.0;
+  if (rew_row || p.ret) {
+    double g_imp = 0.0, g_crew = 0.0;
+    for (int i = 0; i < A; ++i) {
+      const double v = agent_reward<VARIANT>(c, s, r, i);
+      if (rew_row) {
+        if (p.rewards_dtype == SUS_F64) static_cast<double*>(rew_row)[i] = v;
+        else static_cast<float*>(rew_row)[i] = (float)v;
+      }
+      if (p.ret) {  // G = reward + gamma * G (train.py:386); reset to 0 when the episode ends (train.py:436)
+        const double g = __dadd_rn(v, __dmul_rn(p.gamma, p.ret[(int64_t)i * p.N + e]));  // two roundings like numpy, no FMA
+        if ((s.imp >> i) & 1u) g_imp += g; else g_crew += g;
+        p.ret[(int64_t)i * p.N + e] = finished ? 0.0 : g;
+      }
+    }
+    if (p.ret && finished) {  // G[imposter_mask].mean(), G[~imposter_mask].mean() (train.py:421-422)
+      r.ret_imp = g_imp / (double)c.nI;
+      r.ret_crew = g_crew / (double)(A - c.nI);
     }
   }
   if (p.done) p.done[e] = r.done;
@@ -285,6 +299,12 @@ __device__ __forceinline__ void finish_one(const StepParams& p, const GridTables
       // 32 lanes x < 2^26 each cannot overflow 32 bits for any sane episode length
       const uint32_t sum = __reduce_add_sync(kFull, v[k]);
       if (lane == 0 && sum) atomicAdd(p.stats + k, (unsigned long long)sum);
+    }
+    if (p.ret) {
+      double a = r.ret_imp, b = r.ret_crew;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); }
+      if (lane == 0) { atomicAdd(p.ret_sums, a); atomicAdd(p.ret_sums + 1, b); }
     }
   }
   if (stepped) {
@@ -1146,6 +1166,8 @@ struct SusEnv {
   StateArrays st;
   unsigned long long* stats;
   uint32_t* err;
+  double* ret;       // [A][N] + 2 trailing sums, allocated by sus_env_track_returns
+  double gamma;
   uint64_t step_tick, reset_epoch, act_epoch;
   const uint32_t *inj_step, *inj_reset, *inj_act;
 };
@@ -1221,7 +1243,7 @@ int sus_env_destroy(sus_env_t e) {
   DeviceGuard g(e->device);
   cudaDeviceSynchronize();
   cudaFree(e->st.pos); cudaFree(e->st.jobpos); cudaFree(e->st.aux); cudaFree(e->st.met);
-  cudaFree(e->stats); cudaFree(e->err);
+  cudaFree(e->stats); cudaFree(e->err); cudaFree(e->ret);
   delete e;
   return SUS_OK;
 }
@@ -1257,6 +1279,7 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   p.metrics = reinterpret_cast<long long*>(io->metrics); p.imposters = io->imposters; p.spatial = io->spatial; p.non_spatial = io->non_spatial;
   p.inj_step = e->inj_step; p.inj_reset = e->inj_reset; p.inj_act = e->inj_act;
   p.stats = e->stats; p.err = e->err; p.tick = e->step_tick++; p.N = e->N;
+  p.ret = e->ret; p.ret_sums = e->ret ? e->ret + (size_t)e->N * p.c.A : nullptr; p.gamma = e->gamma;
   e->inj_step = e->inj_reset = e->inj_act = nullptr;
   if (e->N == 0) return SUS_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1325,6 +1348,7 @@ int sus_env_rollout(sus_env_t e, int32_t n_steps, double* reward_sums, void* str
   if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
   if (n_steps < 0) return fail(SUS_ERR_INVALID_ARGUMENT, "n_steps < 0");
   if (e->inj_step || e->inj_reset || e->inj_act) return fail(SUS_ERR_INVALID_ARGUMENT, "rollout does not take injected words");
+  if (e->ret) return fail(SUS_ERR_UNSUPPORTED, "rollout does not maintain the tracked returns; use sus_env_step");
   DeviceGuard g(e->device);
   RolloutParams p;
   p.c = e->dc; p.st = e->st; p.stats = e->stats; p.reward_sums = reward_sums; p.tick0 = e->step_tick; p.N = e->N;
@@ -1520,6 +1544,24 @@ int sus_env_clear_stats(sus_env_t e, void* stream) {
   if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
   DeviceGuard g(e->device);
   SUS_CUDA(cudaMemsetAsync(e->stats, 0, SUS_N_STATS * sizeof(int64_t), (cudaStream_t)stream));
+  return SUS_OK;
+}
+
+int sus_env_track_returns(sus_env_t e, double gamma, void* stream) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  DeviceGuard g(e->device);
+  const size_t n = ((size_t)e->N * e->dc.A + 2) * sizeof(double);
+  if (!e->ret) SUS_CUDA(cudaMalloc(&e->ret, n));
+  SUS_CUDA(cudaMemsetAsync(e->ret, 0, n, (cudaStream_t)stream));
+  e->gamma = gamma;
+  return SUS_OK;
+}
+
+int sus_env_return_sums(sus_env_t e, double* out, void* stream) {
+  if (!e || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!e->ret) return fail(SUS_ERR_INVALID_ARGUMENT, "returns are not tracked: call sus_env_track_returns first");
+  DeviceGuard g(e->device);
+  SUS_CUDA(cudaMemcpyAsync(out, e->ret + (size_t)e->N * e->dc.A, 2 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return SUS_OK;
 }
 

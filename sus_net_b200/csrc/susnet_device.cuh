@@ -192,6 +192,7 @@ __device__ __forceinline__ uint32_t n_role_actions(const DevConfig& c, uint32_t 
 struct StepResult {
   uint32_t kill_m, fix_m, sab_m;  // last event ASSIGNED to each agent in this step (base.py:514-515,523,532)
   double team_reward;
+  double ret_imp, ret_crew;  // mean return of the imposters / the crew if the episode ended at this step (else 0)
   bool done, trunc;
 };
 

@@ -21,6 +21,15 @@ def reduce_episode_stats(stats, group=None):
     return out
 
 
+def reduce_return_sums(sums, group=None):
+    """Sum the (2,) float64 [imposter, crew] return sums over all ranks (entries 10 and 11 of the episode-stat vector)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return sums
+    out = sums.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
 def max_over_ranks(value, device=None, group=None):
     """Max of a python float over ranks (bench timing contract)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -294,6 +294,17 @@ class BatchedFourRoomEnv:
             L.check(self.lib.sus_env_clear_stats(self._h, self._stream()))
         return out
 
+    def track_returns(self, gamma):
+        """Keep train()'s running returns `G = reward + gamma * G` (train.py:386) for every agent of every env on the
+        device; finished episodes add G[imposter_mask].mean() / G[~imposter_mask].mean() to `return_sums()`."""
+        L.check(self.lib.sus_env_track_returns(self._h, float(gamma), self._stream()))
+
+    def return_sums(self):
+        """(2,) float64 device tensor: summed imposter / crew returns of the episodes counted in episode_stats()[0]."""
+        out = torch.empty(2, dtype=torch.float64, device=self.device)
+        L.check(self.lib.sus_env_return_sums(self._h, _ptr(out), self._stream()))
+        return out
+
     def episode_stats_dict(self):
         return dict(zip(STAT_KEYS, self.episode_stats().tolist()))
 

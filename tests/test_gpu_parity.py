@@ -423,3 +423,27 @@ def test_unaligned_output_pointers_through_the_c_abi(cuda_lib):
                 # nothing outside the tensors was touched
                 assert (cpu(sp_raw[:off]) == -7).all() and (cpu(sp_raw[off + sp_n:]) == -7).all()
                 assert (cpu(ns_raw[:off]) == -7).all() and (cpu(ns_raw[off + ns_n:]) == -7).all()
+
+
+@pytest.mark.parametrize("name", ["cfg4_base_1v4", "tagging_2v5_short", "base_fixed_order_tsr"])
+def test_tracked_returns_match_oracle(cuda_lib, name):
+    """train()'s running returns G = r + gamma * G per agent (train.py:386) kept on the device: per-episode means summed
+    over finished episodes.  The per-env recurrences are bit-exact; the cross-env sums are order-dependent float adds,
+    compared to 1e-9 relative."""
+    import sus_net_b200 as S
+
+    cfg = CASES[name]
+    N, T, gamma = 3001, 150, 0.9
+    env = make_cuda_env(cfg, N, seed=8)
+    orc = oracle.OracleEnv(cfg, N, seed=8)
+    env.reset(); orc.reset()
+    env.track_returns(gamma); orc.track_returns(gamma)
+    feat = S.GlobalFeaturizer(env)
+    for t in range(T):
+        env.step(None, featurizer=feat if t % 2 else None)
+        orc.step(None)
+    got, want = cpu(env.return_sums()), orc.return_sums()
+    assert int(env.episode_stats()[0]) == int(orc.stats()[0]) > 0
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-9), (got, want)
+    with pytest.raises(NotImplementedError):
+        env.rollout(3)  # the rollout kernel does not maintain tracked returns

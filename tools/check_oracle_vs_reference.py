@@ -87,9 +87,14 @@ def run_case(args):
     orc = oracle.OracleEnv(cfg, n_envs, seed, env_id_base=base)
     f_ref, f_orc = ref.reset(), orc.reset()
     assert np.array_equal(f_ref, f_orc), f"{name}: reset mismatch"
+    gamma = 0.9  # running returns exactly as train() keeps them (train.py:324,386,421-424,436)
+    orc.track_returns(gamma)
+    G = np.zeros((n_envs, ref.A))
+    ret_sums = np.zeros(2)
     assert np.array_equal(ref.imposter_idxs().astype(bool).shape, ref.imposter_idxs().shape)
     episodes = 0
     for t in range(n_steps):
+        prev_imp = np.stack([np.asarray(e.imposter_mask, dtype=bool).copy() for e in ref.envs])
         a_ref = ref.sample_actions()
         a_orc = orc.sample_actions()
         assert np.array_equal(a_ref, a_orc), f"{name}: sample_actions mismatch at step {t}"
@@ -102,6 +107,18 @@ def run_case(args):
         # rewards: bit-exact including the sign of zero
         if not np.array_equal(o_ref["rewards"].view(np.int64), o_orc["rewards"].view(np.int64)):
             raise AssertionError(f"{name}: reward bits mismatch at step {t}")
+        for i, e in enumerate(ref.envs):
+            G[i] = o_ref["rewards"][i] + gamma * G[i]  # train.py:386
+        masks = np.stack([np.zeros(ref.A, dtype=bool)] * n_envs)
+        for i in range(n_envs):  # the roles of the episode that just advanced (pre-reset mask = non-zero rows of o_orc)
+            masks[i] = prev_imp[i]
+        for i in range(n_envs):
+            if o_ref["done"][i] or o_ref["trunc"][i]:
+                ret_sums[0] += G[i][masks[i]].mean().item()  # train.py:421-422
+                ret_sums[1] += G[i][~masks[i]].mean().item()
+                G[i] = 0  # train.py:436
+        assert np.array_equal(G.view(np.int64), orc.returns().view(np.int64)), f"{name}: running returns differ at step {t}"
+        assert np.array_equal(ret_sums.view(np.int64), orc.return_sums().view(np.int64)), f"{name}: return sums differ at step {t}"
         episodes += int(((o_ref["done"] | o_ref["trunc"]) != 0).sum())
         cur_ref, cur_orc = ref.flat_states(), orc.flat_states()
         assert np.array_equal(cur_ref, cur_orc), f"{name}: post-reset state mismatch at step {t}"
