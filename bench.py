@@ -374,7 +374,8 @@ def run_b200_arm(args):
                "single_stream_value": world * N * K / (seq_ms * 1e-3),
                "note": "sus_net_b200.HostStepper: uint8 actions H2D from pinned host memory, fused step+encode, rewards f32 "
                        "+ done + truncated D2H to pinned host memory every step (3 streams, 2 slots); feature tensors stay "
-                       "in HBM for the Q-network"}
+                       "in HBM for the Q-network; no sampler kernel in this loop (the actions arrive from the host), which "
+                       "is why it can exceed `value`"}
         del env, seq
 
     # ---- the one collective of the path: final episode-statistics reduce (NCCL)

@@ -21,12 +21,26 @@ def _nvcc():
     return "nvcc"
 
 
+HASH_FILE = LIB + ".buildhash"
+
+
+def _source_hash():
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for rel in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, rel), "rb") as f:
+            h.update(rel.encode())
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    """Content hash of the sources + flags, not mtimes: a copied tree (gpurun snapshot) must not trigger a rebuild."""
+    if not os.path.exists(LIB) or not os.path.exists(HASH_FILE):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(HASH_FILE) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -42,6 +56,8 @@ def build(force=False, verbose=False):
         raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
     if verbose:
         print(res.stderr, file=sys.stderr)
+    with open(HASH_FILE, "w") as f:
+        f.write(_source_hash())
     return LIB
 
 
