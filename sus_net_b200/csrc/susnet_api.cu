@@ -691,13 +691,22 @@ __global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_step_ws(const __grid_co
 }
 
 __global__ void __launch_bounds__(kThreads) k_sample_actions(const __grid_constant__ ActParams p) {
-  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (e >= p.N) return;
-  const uint32_t imp = (p.st.aux[e].x >> 8) & 0xff;
-  WordStream wa;
-  wa.init(p.c, p.inj_act ? p.inj_act + e * p.c.A : nullptr, (uint32_t)e, p.tick, P_ACT);
-  for (int i = 0; i < p.c.A; ++i)  // base.py:326-330 (R6): dead agents are sampled too
-    p.out[e * p.c.A + i] = (int32_t)bounded(wa.word(i), role_actions_rt(p.c, (imp >> i) & 1u));
+  // each warp's 32 x A action words are contiguous in [N][A]: stage them in shared memory and write them with
+  // lane-contiguous 4-byte stores (A strided stores per lane cost A x the store sectors)
+  __shared__ int32_t stage[kThreads / 32][32 * SUS_MAX_AGENTS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, A = p.c.A;
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x, e0 = e - lane;
+  if (e < p.N) {
+    const uint32_t imp = (p.st.aux[e].x >> 8) & 0xff;
+    WordStream wa;
+    wa.init(p.c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, p.tick, P_ACT);
+    for (int i = 0; i < A; ++i)  // base.py:326-330 (R6): dead agents are sampled too
+      stage[warp][lane * A + i] = (int32_t)bounded(wa.word(i), role_actions_rt(p.c, (imp >> i) & 1u));
+  }
+  __syncwarp();
+  const int64_t rem = p.N - e0;
+  const int n = (int)(rem < 32 ? (rem < 0 ? 0 : rem) : 32) * A;
+  for (int f = lane; f < n; f += 32) p.out[e0 * A + f] = stage[warp][f];
 }
 
 __global__ void __launch_bounds__(kThreads) k_encode_env(const __grid_constant__ EncodeParams p) {
