@@ -13,6 +13,7 @@ from .env import (  # noqa: F401
     StateFields,
 )
 from .featurizers import (  # noqa: F401
+    AgentPositionsFeaturizer,
     AliveCrewFeaturizer,
     ClosestAliveCrewFeaturizer,
     CompositeFeaturizer,
@@ -23,6 +24,7 @@ from .featurizers import (  # noqa: F401
     GlobalFeaturizer,
     ImposterScentFeaturizer,
     ImposterVSCrewRoomLocaionFeaturizer,
+    JobFeaturizer,
     L1CrewFeaturizer,
     OneHotAgentPositionFeaturizer,
     PerspectiveFeaturizer,

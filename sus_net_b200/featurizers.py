@@ -75,6 +75,38 @@ class StateFieldFeaturizer(ComponentFeaturizer):
         return self.env.n_jobs if self.state_field.name == "JOB_STATUS" else self.env.n_agents
 
 
+class _SpatialComponent(ComponentFeaturizer):
+    """The two spatial components of component.py (used by the reference only inside Global / Perspective): featurize ONE
+    state tuple with the Global plane kernel and slice the planes."""
+
+    def _planes(self, state):
+        f = GlobalFeaturizer(self.env)
+        f.fit(torch.as_tensor(self.env.flatten_state(state)).reshape(1, 1, -1))
+        return f.spatial[0, 0]  # (A + 2, 9, 9)
+
+
+class AgentPositionsFeaturizer(_SpatialComponent):
+    """GPU `AgentPositionsFeaturizer` (component.py:83-106): one plane per agent, 1 at (x, y) if alive."""
+
+    def extract_features(self, agent_state, alive_only=True):
+        return self._planes(agent_state)[: self.env.n_agents].clone()
+
+    @property
+    def shape(self):
+        return torch.tensor([self.env.n_agents, self.env.n_cols, self.env.n_rows], dtype=torch.int)
+
+
+class JobFeaturizer(_SpatialComponent):
+    """GPU `JobFeaturizer` (component.py:109-131): plane 0 = incomplete jobs, plane 1 = done jobs."""
+
+    def extract_features(self, agent_state):
+        return self._planes(agent_state)[self.env.n_agents:].clone()
+
+    @property
+    def shape(self):
+        return torch.tensor([2, self.env.n_cols, self.env.n_rows], dtype=torch.int)
+
+
 class CompositeFeaturizer(ComponentFeaturizer):
     """`CompositeFeaturizer` (component.py:134-159): concatenation of flat components in list order."""
 
@@ -116,10 +148,13 @@ class SequenceStateFeaturizer:
 
     _KIND = L.ENCODE_NONE
 
-    def __init__(self, env, clone_views=False):
+    def __init__(self, env, clone_views=False, output_device=None):
         self.env = env
         self.state_size = env.flattened_state_size
         self.clone_views = clone_views  # True: every agent view owns its memory like the reference's .clone()
+        # None: views stay on the env's GPU (for a Q-network on the GPU); "cpu": views are copied to the host, which
+        # is what the reference's unmodified CPU models in src/train.py expect
+        self.output_device = torch.device(output_device) if output_device is not None else None
         self._spec = self._make_spec()
         shape = L.SusEncodeShape()
         L.check(env.lib.sus_encode_shape(C.byref(env._cfg), C.byref(self._spec), C.byref(shape)))
@@ -184,7 +219,9 @@ class SequenceStateFeaturizer:
 
     def _leaf(self, t):
         t = t.detach()
-        if self.clone_views:
+        if self.output_device is not None and t.device != self.output_device:
+            t = t.to(self.output_device)
+        elif self.clone_views:
             t = t.clone()
         return t.requires_grad_(True)
 
@@ -228,9 +265,9 @@ class FlatFeaturizer(SequenceStateFeaturizer):
 
     _KIND = L.ENCODE_FLAT
 
-    def __init__(self, env, featurizer, clone_views=False):
+    def __init__(self, env, featurizer, clone_views=False, output_device=None):
         self.featurizer = featurizer if isinstance(featurizer, CompositeFeaturizer) else CompositeFeaturizer(list(featurizer))
-        super().__init__(env, clone_views=clone_views)
+        super().__init__(env, clone_views=clone_views, output_device=output_device)
 
     def _make_spec(self):
         codes = self.featurizer.codes()
@@ -251,7 +288,8 @@ class FlatFeaturizer(SequenceStateFeaturizer):
         _, ns = self._views()
         out = []
         for _k in range(self.env.n_agents):  # every view is identical (model_ready.py:356-367)
-            out.append((torch.zeros(self.B, self.T, 1, device=self.env.device).requires_grad_(True), self._leaf(ns[0])))
+            dev = self.output_device or self.env.device
+            out.append((torch.zeros(self.B, self.T, 1, device=dev).requires_grad_(True), self._leaf(ns[0])))
         return out
 
     def __repr__(self):

@@ -447,3 +447,27 @@ def test_tracked_returns_match_oracle(cuda_lib, name):
     assert np.allclose(got, want, rtol=1e-9, atol=1e-9), (got, want)
     with pytest.raises(NotImplementedError):
         env.rollout(3)  # the rollout kernel does not maintain tracked returns
+
+
+def test_component_extract_features_and_cpu_output(cuda_lib):
+    """Single-state `extract_features` of the component classes and `output_device="cpu"` (what the reference's unmodified
+    CPU models need) against the oracle."""
+    import sus_net_b200 as S
+
+    cfg = CASES["cfg4_base_1v4"]
+    env = S.FourRoomEnv(1, 4, 5, random_state=5)
+    state, _ = env.reset()
+    for _ in range(7):
+        state, *_ = env.step(env.sample_actions())
+    flat = env.flatten_state(state)[None]
+    sp, ns = oracle.encode_global(cfg, flat)
+    assert np.array_equal(cpu(S.AgentPositionsFeaturizer(env).extract_features(state)), sp[0, :5])
+    assert np.array_equal(cpu(S.JobFeaturizer(env).extract_features(state)), sp[0, 5:])
+    assert S.AgentPositionsFeaturizer(env).shape.tolist() == [5, 9, 9] and S.JobFeaturizer(env).shape.tolist() == [2, 9, 9]
+    one = S.OneHotAgentPositionFeaturizer(env).extract_features(state)
+    assert np.array_equal(cpu(one), oracle.encode_flat(cfg, ["onehot_pos"], flat)[0])
+    f = S.GlobalFeaturizer(env, output_device="cpu")
+    f.fit(torch.tensor(flat, dtype=torch.float64).unsqueeze(0))  # what train.py:346-348 passes
+    views = f.generate_featurized_states()
+    assert all(v[0].device.type == "cpu" and v[1].device.type == "cpu" and v[0].requires_grad for v in views)
+    assert np.array_equal(views[2][0].detach().numpy()[0, 0], sp[0]) and np.array_equal(views[2][1].detach().numpy()[0, 0], ns[2, 0])
