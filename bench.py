@@ -214,6 +214,28 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
+def bind_to_gpu_numa_node(torch_device):
+    """Run this rank on the CPUs NVML reports as local to its GPU (first-touch then places the pinned staging buffers
+    on that NUMA node); matters for the e2e leg when 8 ranks share the host.  Silent no-op if unavailable."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(torch_device).uuid)).encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(torch_device.index)
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpus + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # noqa: BLE001
+        pass
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_b200_arm(args):
     import torch
@@ -230,6 +252,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
+    bind_to_gpu_numa_node(dev)  # pinned host buffers are then allocated next to this GPU's PCIe root
     N, K, W, A = args.envs_per_gpu, args.steps, args.warmup, 5
     seed = 1234
     lib = S.lib()
