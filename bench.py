@@ -252,6 +252,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
+    all_cpus = os.sched_getaffinity(0)
     bind_to_gpu_numa_node(dev)  # pinned host buffers are then allocated next to this GPU's PCIe root
     N, K, W, A = args.envs_per_gpu, args.steps, args.warmup, 5
     seed = 1234
@@ -421,6 +422,7 @@ def run_b200_arm(args):
                       "episode_stats": dict(zip(S.STAT_KEYS, [int(x) for x in stats.tolist()]))},
         }
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line))
     if world > 1:
