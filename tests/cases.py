@@ -63,3 +63,25 @@ def random_case(rng):
     if variant == "training_ground":  # pred_prey.py:52-66 fixes these
         cfg.update(dead_penalty=0.0, is_action_order_random=False, complete_job_reward=3.0, max_time_steps=1000)
     return cfg
+
+
+# extremes of the constructor-argument space (checked oracle-vs-reference by tools/check_oracle_vs_reference.py --edge
+# and CUDA-vs-oracle by tests/test_gpu_parity.py)
+EDGE_CASES = {
+    "edge_max_time_steps_1": default_config("base", n_crew=2, n_jobs=1, max_time_steps=1),
+    "edge_max_time_steps_2_tagging": default_config("tagging", n_crew=3, n_jobs=1, max_time_steps=2, tag_reset_interval=1),
+    "edge_tag_interval_1": default_config("tagging", n_imposters=3, n_crew=4, n_jobs=2, tag_reset_interval=1, max_time_steps=30),
+    "edge_largest_8_agents_8_jobs_tagging": default_config("tagging", n_imposters=3, n_crew=5, n_jobs=8, tag_reset_interval=3,
+                                                           max_time_steps=40, include_walls=False),
+    "edge_all_zero_rewards": default_config("base", n_crew=3, n_jobs=2, kill_reward=0.0, complete_job_reward=0.0,
+                                            sabotage_reward=0.0, game_end_reward=0.0, dead_penalty=0.0, time_step_reward=0.0,
+                                            max_time_steps=25),
+    "edge_negative_zero_tagging": default_config("tagging", n_crew=2, n_jobs=1, kill_reward=0.0, complete_job_reward=0.0,
+                                                 sabotage_reward=0.0, game_end_reward=0.0, dead_penalty=0.0,
+                                                 time_step_reward=0.0, vote_reward=0.0, tag_reset_interval=2, max_time_steps=20),
+    "edge_itg_1v7": default_config("training_ground", n_crew=7, n_jobs=8, kill_reward=-3.0, sabotage_reward=0.0,
+                                   game_end_reward=2.5, time_step_reward=-0.125, shuffle_imposter_index=True),
+    "edge_single_job_single_crew_itg": default_config("training_ground", n_crew=1, n_jobs=1, kill_reward=1.5,
+                                                      sabotage_reward=0.0, game_end_reward=-4.0, time_step_reward=0.0,
+                                                      include_walls=False),
+}

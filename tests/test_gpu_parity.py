@@ -471,3 +471,42 @@ def test_component_extract_features_and_cpu_output(cuda_lib):
     views = f.generate_featurized_states()
     assert all(v[0].device.type == "cpu" and v[1].device.type == "cpu" and v[0].requires_grad for v in views)
     assert np.array_equal(views[2][0].detach().numpy()[0, 0], sp[0]) and np.array_equal(views[2][1].detach().numpy()[0, 0], ns[2, 0])
+
+
+def _edge_names():
+    from tests.cases import EDGE_CASES
+
+    return list(EDGE_CASES)
+
+
+@pytest.mark.parametrize("name", _edge_names())
+def test_edge_case_configs_match_oracle(cuda_lib, name):
+    """Extremes of the constructor-argument space (oracle pinned vs the reference: profiles/r01_oracle_pin_edge_cases.log):
+    1-step episodes, 1-step vote windows, 8 agents x 8 jobs, all-zero rewards (-0.0 in the tagging env)."""
+    import sus_net_b200 as S
+    from tests.cases import EDGE_CASES
+
+    cfg = EDGE_CASES[name]
+    N, T = 515, 120
+    env = make_cuda_env(cfg, N, seed=12)
+    env._rewards = torch.zeros((N, env.n_agents), dtype=torch.float64, device=env.device)
+    env._metrics_buf = torch.zeros((N, 8), dtype=torch.int64, device=env.device)
+    orc = oracle.OracleEnv(cfg, N, seed=12)
+    assert np.array_equal(cpu(env.reset()[0]).astype(np.int64), orc.reset())
+    feat = S.PerspectiveFeaturizer(env) if cfg["n_jobs"] > 0 else None
+    for t in range(T):
+        acts = env.sample_actions().clone() if t % 2 else None
+        if acts is not None:
+            assert np.array_equal(cpu(acts), orc.sample_actions())
+        nf, r, d, tr, _ = env.step(acts, featurizer=feat)
+        o = orc.step(None if acts is None else cpu(acts))
+        assert np.array_equal(cpu(nf).astype(np.int64), o["next_flat"]), f"state differs at step {t}"
+        assert np.array_equal(reward_bits(cpu(r)), reward_bits(o["rewards"])), f"reward bits differ at step {t}"
+        assert np.array_equal(cpu(d), o["done"] != 0) and np.array_equal(cpu(tr), o["trunc"] != 0)
+        assert np.array_equal(cpu(env._metrics_buf), o["metrics"])
+    cur = orc.flat_states()
+    assert np.array_equal(cpu(env.flat_states(torch.int64)), cur) and np.array_equal(cpu(env.episode_stats()), orc.stats())
+    if feat is not None:
+        sp, ns = oracle.encode_perspective(cfg, cur)
+        views = feat.generate_featurized_states()
+        assert all(np.array_equal(cpu(v[0])[:, 0], sp[i]) and np.array_equal(cpu(v[1])[:, 0], ns[i]) for i, v in enumerate(views))

@@ -76,7 +76,11 @@ def run_case(args):
     from oracle import ref_harness as H
 
     oracle.set_threads(1)
-    if isinstance(name, tuple):  # ("random", k): k-th random constructor-argument set
+    if isinstance(name, tuple) and name[0] == "edge":
+        from tests.cases import EDGE_CASES
+
+        cfg, name = EDGE_CASES[name[1]], name[1]
+    elif isinstance(name, tuple):  # ("random", k): k-th random constructor-argument set
         from tests.cases import random_case
 
         cfg = random_case(np.random.default_rng(100000 + name[1]))
@@ -139,11 +143,16 @@ def main():
     ap.add_argument("--procs", type=int, default=os.cpu_count())
     ap.add_argument("--seed", type=int, default=20260)
     ap.add_argument("--shards", type=int, default=1, help="independent env-id shards per case")
+    ap.add_argument("--edge", action="store_true", help="check tests.cases.EDGE_CASES instead")
     ap.add_argument("--random-configs", type=int, default=0, help="check this many random constructor-argument sets instead")
     a = ap.parse_args()
     names = [a.case] if a.case else list(CASES)
     if a.random_configs:
         names = [("random", k) for k in range(a.random_configs)]
+    if a.edge:
+        from tests.cases import EDGE_CASES
+
+        names = [("edge", k) for k in EDGE_CASES]
     jobs = [(n, a.envs, a.steps, a.seed, s * a.envs) for n in names for s in range(a.shards)]
     t0 = time.time()
     with mp.Pool(a.procs) as pool:
