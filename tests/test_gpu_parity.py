@@ -510,3 +510,23 @@ def test_edge_case_configs_match_oracle(cuda_lib, name):
         sp, ns = oracle.encode_perspective(cfg, cur)
         views = feat.generate_featurized_states()
         assert all(np.array_equal(cpu(v[0])[:, 0], sp[i]) and np.array_equal(cpu(v[1])[:, 0], ns[i]) for i, v in enumerate(views))
+
+
+def test_cfg2_4096_envs_10k_trajectories_bit_exact(cuda_lib):
+    """BASELINE.json configs[1]: ImposterTrainingGround 1v1 on the walled grid, 4096 batched envs, every trajectory run to
+    done / truncation, > 10 000 finished trajectories, every step compared (state, rewards, done, truncated).  The same
+    configuration is pinned oracle-vs-reference on > 10 000 trajectories in profiles/r01_oracle_pin_cfg2_10k_trajectories.log."""
+    cfg = CASES["cfg2_itg_1v1_wall"]
+    N, T = 4096, 1500
+    env = make_cuda_env(cfg, N, seed=2, env_id_base=0)
+    orc = oracle.OracleEnv(cfg, N, seed=2, env_id_base=0)
+    assert np.array_equal(cpu(env.reset()[0]).astype(np.int64), orc.reset())
+    out = None
+    for t in range(T):
+        nf, r, d, tr, _ = env.step(None)
+        out = orc.step(None, out=out)
+        assert np.array_equal(cpu(nf).astype(np.int64), out["next_flat"]), f"state differs at step {t}"
+        assert np.array_equal(cpu(r), out["rewards"].astype(np.float32)), f"rewards differ at step {t}"
+        assert np.array_equal(cpu(d), out["done"] != 0) and np.array_equal(cpu(tr), out["trunc"] != 0)
+    stats = cpu(env.episode_stats())
+    assert np.array_equal(stats, orc.stats()) and stats[0] > 10_000, stats
