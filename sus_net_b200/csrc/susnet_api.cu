@@ -439,7 +439,6 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_tma(const __grid_
   const int64_t n_groups = (p.N + 31) >> 5;
   const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
   const int64_t g_stride = (int64_t)gridDim.x * L.warps;
-  if (L.stagger_ns > 0 && warp > 0) __nanosleep((unsigned)(warp * L.stagger_ns));
   StepInput in, in_next;
   {
     const int64_t g = (int64_t)blockIdx.x * L.warps + warp;
@@ -1077,8 +1076,6 @@ bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool wa
     if (!force_g && best.warps >= 8) break;  // G = 8 tiles with >= 8 warps measured best; otherwise try G = 4
   }
   if (best.warps < 2) return false;
-  const char* env_s = std::getenv("SUSNET_STAGGER_NS");
-  best.stagger_ns = env_s ? std::atoi(env_s) : 0;
   L = best;
   return true;
 }

@@ -23,7 +23,6 @@ struct TileLayout {
   int32_t nf_off, nf_bytes;    // next_flat         [32][S] f32
   int32_t per_warp;            // total bytes per warp
   int32_t warps;               // warps per CTA
-  int32_t stagger_ns;          // warp w starts w * stagger_ns late (de-synchronises the warps' compute / store phases)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
