@@ -241,6 +241,10 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
 
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        from sus_net_b200 import build as B
+
+        B.build()  # no-op when the in-tree library matches the sources; compiles on a fresh checkout (needs nvcc)
     import sus_net_b200 as S
     from sus_net_b200.distributed import max_over_ranks, reduce_episode_stats
 
