@@ -241,10 +241,14 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
 
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        from sus_net_b200 import build as B
+    from sus_net_b200 import build as B
 
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         B.build()  # no-op when the in-tree library matches the sources; compiles on a fresh checkout (needs nvcc)
+    else:
+        t_wait = time.time()
+        while B.needs_build() and time.time() - t_wait < 900:  # local rank 0 is compiling
+            time.sleep(1.0)
     import sus_net_b200 as S
     from sus_net_b200.distributed import max_over_ranks, reduce_episode_stats
 
