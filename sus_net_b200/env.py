@@ -175,6 +175,7 @@ class BatchedFourRoomEnv:
         self.emit_imposters = False   # batched mode: also write the (N, n_imposters) int16 replay column
         self._imposters_buf = None
         self._last_actions = None     # (N, A) int32: the actions the last fused-random-policy step applied
+        self._applied_actions = None  # the (N, A) device tensor the last step consumed (what a replay ring stores)
         self._host_state = None  # reference mode: numpy mirror of the single env
         self._imp_cache = None
         self._was_reset = False
@@ -447,6 +448,7 @@ class BatchedFourRoomEnv:
                 if self._last_actions is None:
                     self._last_actions = torch.zeros((N, A), dtype=torch.int32, device=self.device)
                 io.actions_out = self._last_actions.data_ptr()
+                self._applied_actions = self._last_actions
         else:
             if not self.batched:
                 assert len(agent_actions) == A, f"Expected {A} actions, got {len(agent_actions)}"  # base.py:357-359
@@ -466,6 +468,7 @@ class BatchedFourRoomEnv:
             assert tuple(keep.shape) == (N, A), f"Expected actions of shape {(N, A)}, got {tuple(keep.shape)}"
             io.actions = keep.data_ptr()
             io.actions_dtype = _TORCH_TO_SUS[keep.dtype]
+            self._applied_actions = keep
         rewards, done, trunc = (self._rewards, self._done, self._trunc) if out is None else out
         io.rewards = rewards.data_ptr()
         io.rewards_dtype = _TORCH_TO_SUS[rewards.dtype]

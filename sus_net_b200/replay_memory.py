@@ -125,7 +125,7 @@ class ReplayBuffer:
         env = self._env
         out = env.step(actions, featurizer=featurizer)
         next_flat, rewards, dones, truncated, _ = out
-        applied = env._last_actions if actions is None else out_actions(actions, env)
+        applied = env._applied_actions  # the device tensor the step consumed (given, converted, or drawn by the policy)
         env.flat_states(out=self._cur_flat)
         N = env.num_envs
         p = L.SusReplayPush(
@@ -142,11 +142,3 @@ class ReplayBuffer:
         self.size = min(self.size + N, self.max_size)
         return out
 
-
-def out_actions(actions, env):
-    """The (N, A) device tensor the step consumed (int32 / int64 / uint8, contiguous)."""
-    if isinstance(actions, torch.Tensor) and actions.device == env.device and actions.is_contiguous() and \
-            actions.dtype in (torch.uint8, torch.int32, torch.int64):
-        return actions
-    return torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions).to(
-        device=env.device, dtype=torch.int32).contiguous()
