@@ -217,6 +217,12 @@ class SequenceStateFeaturizer:
         ns = self._ns_buf.view(sh.non_spatial_views, self.B, self.T, sh.non_spatial_floats)
         return sp, ns
 
+    def stacked_views(self):
+        """The featurized tensors of the last fit / encode without per-agent slicing: `(spatial, non_spatial)` with
+        shapes (Vs, B, T, C, 9, 9) or None and (Vn, B, T, F); Vs / Vn are 1 where all agent views share the tensor."""
+        sp, ns = self._views()
+        return sp, ns
+
     def _leaf(self, t):
         t = t.detach()
         if self.output_device is not None and t.device != self.output_device:

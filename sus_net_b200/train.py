@@ -45,6 +45,40 @@ class BatchedActor:
         self.generator, self.dense = generator, dense
 
     @torch.no_grad()
+    def act_grouped(self, featurizer, eps, flat_states):
+        """Sync-free acting for n_imposters == 1 on the featurizer's stacked views: the imposter network runs ONCE on N
+        rows (row e = the view of env e's imposter), the crew network once per agent view on all N rows, and the per-env
+        choice is made with `torch.where`.  Same distribution as `act`; identical actions for eps == 0."""
+        env = self.env
+        assert env.n_imposters == 1
+        sp, ns = featurizer.stacked_views()
+        N, A, dev = flat_states.shape[0], env.n_agents, flat_states.device
+        alive = flat_states[:, 2 * A:3 * A] != 0
+        imp = env.imposter_mask_batch
+        imp_idx = torch.argmax(imp.to(torch.uint8), dim=1)  # the single imposter of every env, no host sync
+        rows = torch.arange(N, device=dev)
+
+        def view(t, k):  # tensor of agent view k (k: int or per-env index tensor)
+            if t is None:
+                return torch.zeros(N, featurizer.T, 1, device=dev)  # FlatFeaturizer's spatial placeholder
+            if t.shape[0] == 1:
+                return t[0]
+            return t[k, rows] if isinstance(k, torch.Tensor) else t[k]
+
+        def choose(model, n_act, spatial, non_spatial):
+            explore = torch.rand(N, device=dev, generator=self.generator) <= eps
+            rand_a = torch.randint(0, n_act, (N,), device=dev, generator=self.generator)
+            return torch.where(explore, rand_a, torch.argmax(model(spatial, non_spatial), dim=1))
+
+        a_imp = choose(self.imposter_model, env.n_imposter_actions, view(sp, imp_idx), view(ns, imp_idx))
+        actions = torch.zeros((N, A), dtype=torch.int32, device=dev)
+        for k in range(A):
+            a_crew = choose(self.crew_model, env.n_crew_actions, view(sp, k), view(ns, k))
+            a = torch.where(imp[:, k], a_imp, a_crew)
+            actions[:, k] = torch.where(alive[:, k], a, torch.zeros_like(a)).to(torch.int32)
+        return actions
+
+    @torch.no_grad()
     def act(self, views, eps, flat_states, imposter_mask=None):
         """views: featurizer.generate_featurized_states(); flat_states (N, S): the states the views were made from
         (alive flags live at [2A, 3A)); returns (N, A) int32 role-list indices."""
@@ -165,8 +199,10 @@ def train_batched(env, replay_buffer, featurizer, imposter_model, crew_model, tr
             crew_target.load_state_dict(crew_model.state_dict())
         seq = replay_buffer.state_sequence
         featurizer.fit(seq)  # train.py:346-348
-        views = featurizer.generate_featurized_states()
-        actions = actor.act(views, scheduler.value(it), seq[:, -1])
+        if env.n_imposters == 1:
+            actions = actor.act_grouped(featurizer, scheduler.value(it), seq[:, -1])
+        else:
+            actions = actor.act(featurizer.generate_featurized_states(), scheduler.value(it), seq[:, -1])
         replay_buffer.collect_step(actions)  # env.step + replay add (train.py:383-399)
         if it % train_step_interval == 0:  # train.py:402-416
             batch = replay_buffer.sample(batch_size, generator=generator)

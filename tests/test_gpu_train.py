@@ -91,6 +91,7 @@ def test_batched_training_loop_runs_and_acts_within_role_ranges(cuda_lib):
     alive = seq[:, -1, 10:15] != 0
     mask = env.imposter_mask_batch
     assert (acts[~alive] == 0).all() and (acts[mask].max() <= 5) and (acts[~mask].max() <= 4)
+    assert torch.equal(acts, S.BatchedActor(env, imp, crew).act_grouped(feat, 0.0, seq[:, -1]))  # sync-free variant
     k = 2
     want = torch.argmax(imp(views[k][0], views[k][1]), dim=1)
     sel = mask[:, k] & alive[:, k]
