@@ -530,3 +530,40 @@ def test_cfg2_4096_envs_10k_trajectories_bit_exact(cuda_lib):
         assert np.array_equal(cpu(d), out["done"] != 0) and np.array_equal(cpu(tr), out["trunc"] != 0)
     stats = cpu(env.episode_stats())
     assert np.array_equal(stats, orc.stats()) and stats[0] > 10_000, stats
+
+
+def test_env_on_a_non_current_device_and_side_stream(cuda_lib):
+    """The handle remembers its device (every C-ABI call switches to it and back) and all launches go to the caller's
+    current stream: an env on cuda:1 driven while cuda:0 is current, and an env driven on a side stream, reproduce the
+    default-stream env on cuda:0."""
+    import sus_net_b200 as S
+
+    cfg = CASES["cfg4_base_1v4"]
+    N, T = 4096, 25
+    ref = make_cuda_env(cfg, N, seed=6, device="cuda:0")
+    ref.reset()
+    fr = S.GlobalFeaturizer(ref)
+    for _ in range(T):
+        ref.step(None, featurizer=fr)
+    torch.cuda.synchronize()
+    want_state, want_sp = ref.flat_states(torch.int64).cpu(), fr.spatial.detach().cpu()
+    # side stream on the same device
+    side = torch.cuda.Stream("cuda:0")
+    with torch.cuda.stream(side):
+        e2 = make_cuda_env(cfg, N, seed=6, device="cuda:0")
+        e2.reset()
+        f2 = S.GlobalFeaturizer(e2)
+        for _ in range(T):
+            e2.step(None, featurizer=f2)
+        got_state, got_sp = e2.flat_states(torch.int64), f2.spatial.detach()
+    side.synchronize()
+    assert torch.equal(got_state.cpu(), want_state) and torch.equal(got_sp.cpu(), want_sp)
+    if torch.cuda.device_count() >= 2:
+        assert torch.cuda.current_device() == 0
+        e3 = make_cuda_env(cfg, N, seed=6, device="cuda:1")
+        e3.reset()
+        f3 = S.GlobalFeaturizer(e3)
+        for _ in range(T):
+            e3.step(None, featurizer=f3)
+        assert torch.cuda.current_device() == 0
+        assert torch.equal(e3.flat_states(torch.int64).cpu(), want_state) and torch.equal(f3.spatial.detach().cpu(), want_sp)
