@@ -567,3 +567,34 @@ def test_env_on_a_non_current_device_and_side_stream(cuda_lib):
             e3.step(None, featurizer=f3)
         assert torch.cuda.current_device() == 0
         assert torch.equal(e3.flat_states(torch.int64).cpu(), want_state) and torch.equal(f3.spatial.detach().cpu(), want_sp)
+
+
+def test_action_dtypes_and_invalid_indices(cuda_lib):
+    """uint8 / int32 / int64 action tensors give identical steps; an index outside an agent's role list (or negative, or
+    >= 256) leaves that env untouched and is reported by check_actions() as the reference's IndexError."""
+    cfg = CASES["cfg3_tagging_1v2"]
+    N = 2000
+    envs = [make_cuda_env(cfg, N, seed=4) for _ in range(3)]
+    for e in envs:
+        e.reset()
+    for t in range(30):
+        a = envs[0].sample_actions().clone()
+        outs = [e.step(a.to(dt)) for e, dt in zip(envs, (torch.int32, torch.int64, torch.uint8))]
+        assert all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2]) for o in outs[1:])
+        for e in envs[1:]:
+            e.sample_actions()  # keep the act epochs aligned
+    env = envs[0]
+    before = env.flat_states(torch.int64).clone()
+    a = env.sample_actions().clone().to(torch.int64)
+    bad_rows = torch.tensor([3, 77, 1999], device=env.device)
+    a[bad_rows[0], 1] = 9          # past every role list of a 3-agent tagging env (8 or 9 entries)
+    a[bad_rows[1], 0] = -1         # negative
+    a[bad_rows[2], 2] = 300        # >= 256
+    env.step(a)
+    after = env.flat_states(torch.int64)
+    assert torch.equal(after[bad_rows], before[bad_rows])  # rejected envs did not move
+    changed = (after != before).any(dim=1)
+    assert changed.sum() > N // 2
+    with pytest.raises(IndexError):
+        env.check_actions()
+    env.check_actions()  # the counter was cleared
