@@ -211,12 +211,12 @@ __device__ __forceinline__ void unpack_state(const StepInput& in, EnvState& s) {
 // ---- the step of one env, shared by the direct-store kernel (k_step) and the TMA-staged kernel (k_step_tma).
 // rew_row / nf_row point at THIS env's reward / next_flat row: in global memory (direct) or in the warp's
 // shared-memory staging block (TMA path).
-template <int VARIANT>
+template <int VARIANT, int TA = 0, int TJ = 0>
 __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& tb, int64_t e, bool have,
                                          const StepInput& in, void* rew_row, float* nf_row, EnvState& s, StepResult& r,
                                          bool& stepped, bool& finished) {
   const DevConfig& c = p.c;
-  const int A = c.A;
+  const int A = TA ? TA : c.A;
   stepped = false;
   finished = false;
   if (!have) return;
@@ -242,7 +242,7 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
   }
   WordStream ws;
   ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, p.tick, P_STEP);
-  step_env<VARIANT>(c, tb, s, acts, ws, r);
+  step_env<VARIANT, TA, TJ>(c, tb, s, acts, ws, r);
   stepped = true;
   finished = r.done || r.trunc;
   r.ret_imp = r.ret_crew = 0.0;
@@ -321,7 +321,7 @@ __device__ __forceinline__ void finish_one(const StepParams& p, const GridTables
 
 // K1 (+K2), direct-store path: one thread per env, outputs written straight from registers.  Used for ragged or
 // unaligned outputs and as the fallback when the staging tiles do not fit in shared memory.
-template <int VARIANT, bool ENCODE>
+template <int VARIANT, bool ENCODE, int TA = 0, int TJ = 0>
 __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepParams p) {
   __shared__ GridTables tb;
   stage_tables(p.c, tb);
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepP
   StepResult r = {};
   StepInput in;
   load_input(p, e, have, in);
-  step_one<VARIANT>(p, tb, e, have, in,
+  step_one<VARIANT, TA, TJ>(p, tb, e, have, in,
                     p.rewards ? static_cast<uint8_t*>(p.rewards) + e * p.c.A * (p.rewards_dtype == SUS_F64 ? 8 : 4) : nullptr,
                     p.next_flat ? p.next_flat + e * p.c.S : nullptr, s, r, stepped, finished);
   finish_one(p, tb, e, lane, s, r, stepped, finished);
@@ -358,12 +358,12 @@ struct RolloutParams {
   int32_t n_steps;
 };
 
-template <int VARIANT>
+template <int VARIANT, int TA = 0, int TJ = 0>
 __global__ void __launch_bounds__(kThreads) k_rollout(const __grid_constant__ RolloutParams p) {
   __shared__ GridTables tb;
   stage_tables(p.c, tb);
   const DevConfig& c = p.c;
-  const int A = c.A, lane = threadIdx.x & 31;
+  const int A = TA ? TA : c.A, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const bool have = e < p.N;
   EnvState s = {};
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kThreads) k_rollout(const __grid_constant__ Ro
       WordStream ws;
       ws.init(c, nullptr, (uint32_t)e, tick, P_STEP);
       StepResult r = {};
-      step_env<VARIANT>(c, tb, s, acts, ws, r);
+      step_env<VARIANT, TA, TJ>(c, tb, s, acts, ws, r);
       if (p.reward_sums) {
 #pragma unroll
         for (int i = 0; i < SUS_MAX_AGENTS; ++i)
@@ -1338,15 +1338,27 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
     return after_launch("k_step_tma");
   }
   const unsigned gr = grid_for(e->N);
+  const int dA = p.c.A, dJ = p.c.J;
+  // step-only launches of the common shapes use instantiations with compile-time agent / job counts
+#define SUS_LAUNCH_STEP_ONLY(V)                                                                   \
+  if (dA == 5 && dJ == 5) k_step<V, false, 5, 5><<<gr, kThreads, 0, st>>>(p);                     \
+  else if (dA == 3 && dJ == 5) k_step<V, false, 3, 5><<<gr, kThreads, 0, st>>>(p);                \
+  else k_step<V, false><<<gr, kThreads, 0, st>>>(p)
 #define SUS_LAUNCH_STEP(V)                                      \
   if (enc) k_step<V, true><<<gr, kThreads, 0, st>>>(p);         \
-  else k_step<V, false><<<gr, kThreads, 0, st>>>(p)
+  else { SUS_LAUNCH_STEP_ONLY(V); }
   switch (e->cfg.variant) {
     case SUS_VARIANT_BASE: SUS_LAUNCH_STEP(SUS_VARIANT_BASE); break;
     case SUS_VARIANT_TAGGING: SUS_LAUNCH_STEP(SUS_VARIANT_TAGGING); break;
-    default: SUS_LAUNCH_STEP(SUS_VARIANT_TRAINING_GROUND); break;
+    default:
+      if (enc) k_step<SUS_VARIANT_TRAINING_GROUND, true><<<gr, kThreads, 0, st>>>(p);
+      else if (dA == 2 && dJ == 0) k_step<SUS_VARIANT_TRAINING_GROUND, false, 2, 0><<<gr, kThreads, 0, st>>>(p);
+      else if (dA == 5 && dJ == 0) k_step<SUS_VARIANT_TRAINING_GROUND, false, 5, 0><<<gr, kThreads, 0, st>>>(p);
+      else k_step<SUS_VARIANT_TRAINING_GROUND, false><<<gr, kThreads, 0, st>>>(p);
+      break;
   }
 #undef SUS_LAUNCH_STEP
+#undef SUS_LAUNCH_STEP_ONLY
   return after_launch("k_step");
 }
 
@@ -1363,11 +1375,21 @@ int sus_env_rollout(sus_env_t e, int32_t n_steps, double* reward_sums, void* str
   if (e->N == 0 || n_steps == 0) return SUS_OK;
   const unsigned gr = grid_for(e->N);
   cudaStream_t st = (cudaStream_t)stream;
+  const int dA = p.c.A, dJ = p.c.J;
+#define SUS_LAUNCH_ROLLOUT(V)                                                             \
+  if (dA == 5 && dJ == 5) k_rollout<V, 5, 5><<<gr, kThreads, 0, st>>>(p);                 \
+  else if (dA == 3 && dJ == 5) k_rollout<V, 3, 5><<<gr, kThreads, 0, st>>>(p);            \
+  else k_rollout<V><<<gr, kThreads, 0, st>>>(p)
   switch (e->cfg.variant) {
-    case SUS_VARIANT_BASE: k_rollout<SUS_VARIANT_BASE><<<gr, kThreads, 0, st>>>(p); break;
-    case SUS_VARIANT_TAGGING: k_rollout<SUS_VARIANT_TAGGING><<<gr, kThreads, 0, st>>>(p); break;
-    default: k_rollout<SUS_VARIANT_TRAINING_GROUND><<<gr, kThreads, 0, st>>>(p); break;
+    case SUS_VARIANT_BASE: SUS_LAUNCH_ROLLOUT(SUS_VARIANT_BASE); break;
+    case SUS_VARIANT_TAGGING: SUS_LAUNCH_ROLLOUT(SUS_VARIANT_TAGGING); break;
+    default:
+      if (dA == 2 && dJ == 0) k_rollout<SUS_VARIANT_TRAINING_GROUND, 2, 0><<<gr, kThreads, 0, st>>>(p);
+      else if (dA == 5 && dJ == 0) k_rollout<SUS_VARIANT_TRAINING_GROUND, 5, 0><<<gr, kThreads, 0, st>>>(p);
+      else k_rollout<SUS_VARIANT_TRAINING_GROUND><<<gr, kThreads, 0, st>>>(p);
+      break;
   }
+#undef SUS_LAUNCH_ROLLOUT
   return after_launch("k_rollout");
 }
 
