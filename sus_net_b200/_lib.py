@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsusnet_b200.so")
+LIB_PATH = os.environ.get("SUSNET_B200_LIB") or os.path.join(HERE, "libsusnet_b200.so")  # override: A/B builds
 
 SUS_OK, SUS_ERR_INVALID_ARGUMENT, SUS_ERR_UNSUPPORTED, SUS_ERR_CUDA, SUS_ERR_INVALID_ACTION = 0, -1, -2, -3, -4
 VARIANT_BASE, VARIANT_TAGGING, VARIANT_TRAINING_GROUND = 0, 1, 2
