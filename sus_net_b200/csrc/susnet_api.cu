@@ -344,6 +344,95 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepP
   }
 }
 
+// Per-warp staging block of k_step_flat (bytes; offsets are multiples of 16)
+struct FlatStage {
+  int32_t row_bytes;  // 32 rows x F bytes, rounded up to 16
+  int32_t rew_off, nf_off, per_warp;
+};
+
+// Copy `n_words` 32-bit words from a warp's staging block to global memory with lane-contiguous stores
+// (128-bit when both sides are 16-byte aligned).  All 32 lanes.
+__device__ __forceinline__ void warp_copy_words(uint32_t* __restrict__ g, const uint32_t* __restrict__ s, int n_words, int lane) {
+  int done = 0;
+  if (((uint32_t)reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+    const int n4 = n_words >> 2;
+    for (int i = lane; i < n4; i += 32) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(s)[i];
+    done = n4 << 2;
+  }
+  for (int i = done + lane; i < n_words; i += 32) g[i] = s[i];
+}
+
+// K1+K2 for FLAT encodes (the reference's training recipes: one-hot positions + crew flags, component.py): one thread
+// per env at high occupancy.  A flat row is F mostly-zero small integers, so each warp stages its 32 rows as ONE BYTE
+// per value (prefilled with the byte of 0; the one-hot segments only set their ones), then all lanes expand the
+// 32 x F bytes to floats with lane-contiguous 128-bit stores.  32 F bytes of shared memory per warp instead of the
+// 128 F of the TMA staging rows is what lifts the occupancy from 16 to 32 warps per SM; the step is latency-bound
+// (measured: time ~ 0.06 ms + 1.0 ms / warps per SM at 1 Mi envs), so occupancy is what pays.  Rewards and the replay
+// row are staged as words and leave the same way.
+constexpr int kFlatMinCtas = 4;
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads, kFlatMinCtas) k_step_flat(const __grid_constant__ StepParams p,
+                                                                       const __grid_constant__ FlatStage L) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ GridTables tb;
+  stage_tables(p.c, tb);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int A = p.c.A, S = p.c.S, F = p.enc.ns_floats;
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x, e0 = e - lane;
+  if (e0 >= p.N) return;  // whole warp
+  const bool have = e < p.N;
+  const int cnt = p.N - e0 < 32 ? (int)(p.N - e0) : 32;
+  uint8_t* blk = dyn_smem + (size_t)warp * L.per_warp;
+  {
+    const uint32_t z = kByteRowBias * 0x01010101u;
+    for (int i = lane; i < (L.row_bytes >> 4); i += 32) reinterpret_cast<uint4*>(blk)[i] = make_uint4(z, z, z, z);
+  }
+  const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
+  uint8_t* rew = blk + L.rew_off;
+  float* nf = reinterpret_cast<float*>(blk + L.nf_off);
+  bool stepped, finished;
+  EnvState s = {};
+  StepResult r = {};
+  StepInput in;
+  load_input(p, e, have, in);
+  step_one<VARIANT>(p, tb, e, have, in, p.rewards ? rew + lane * A * rew_elem : nullptr, p.next_flat ? nf + lane * S : nullptr,
+                    s, r, stepped, finished);
+  finish_one(p, tb, e, lane, s, r, stepped, finished);
+  __syncwarp();  // the prefill is complete before any lane sets bytes in its row
+  if (have) flat_row<ByteRow>(p.c, p.enc, tb, obs_of(s), blk + lane * F);
+  const bool all_stepped = __all_sync(kFull, stepped || !have);  // (also orders the staged rows before the reads below)
+  if (all_stepped) {
+    if (p.rewards)
+      warp_copy_words(reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.rewards) + e0 * A * rew_elem),
+                      reinterpret_cast<const uint32_t*>(rew), cnt * A * rew_elem / 4, lane);
+    if (p.next_flat) warp_copy_words(reinterpret_cast<uint32_t*>(p.next_flat + e0 * S), reinterpret_cast<const uint32_t*>(nf), cnt * S, lane);
+  } else if (stepped) {  // rare: an env of the group had its actions rejected and keeps its old outputs
+    if (p.rewards) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(rew + lane * A * rew_elem);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.rewards) + e * A * rew_elem);
+      for (int i = 0; i < A * rew_elem / 4; ++i) dst[i] = src[i];
+    }
+    if (p.next_flat)
+      for (int i = 0; i < S; ++i) p.next_flat[e * S + i] = nf[lane * S + i];
+  }
+  // expand the byte rows: word i of the block holds floats [4i, 4i + 4) of the warp's cnt x F output floats
+  float* out = p.non_spatial + e0 * F;
+  const int n = cnt * F;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(blk);
+  int done = 0;
+  if (((uint32_t)reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const int n4 = n >> 2;
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+      const uint32_t x = w[i];
+      reinterpret_cast<float4*>(out)[i] =
+          make_float4(byte_row_value(x, 0), byte_row_value(x, 1), byte_row_value(x, 2), byte_row_value(x, 3));
+    }
+    done = n4 << 2;
+  }
+  for (int i = done + lane; i < n; i += 32) out[i] = byte_row_value(w[i >> 2], i & 3);
+}
+
 // Random-policy rollout: every env advances `n_steps` steps inside ONE launch with its state in registers
 // (== n_steps calls of step(None): same ticks, same draws, same auto-resets, same episode statistics); only the final
 // state and, optionally, the per-agent reward sums are written.  This is ReplayBuffer.populate's / a random-policy
@@ -1080,6 +1169,19 @@ bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool wa
   return true;
 }
 
+// Staged-bytes layout of k_step_flat; false if a component is float-valued or kFlatMinCtas CTAs do not fit on an SM.
+bool make_flat_stage(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, FlatStage& L) {
+  if (enc.kind != SUS_ENCODE_FLAT) return false;
+  for (int q = 0; q < enc.n_components; ++q)
+    if (enc.components[q] == SUS_FC_SCENT) return false;
+  L.row_bytes = (32 * enc.ns_floats + 15) & ~15;
+  L.rew_off = L.row_bytes;
+  L.nf_off = L.rew_off + ((32 * c.A * rew_elem + 15) & ~15);
+  L.per_warp = L.nf_off + (want_nf ? (32 * c.S * 4 + 15) & ~15 : 0);
+  const size_t per_cta = (size_t)L.per_warp * (kThreads / 32) + 1024;  // + static tables and the driver's reserve
+  return per_cta <= (size_t)max_dyn_smem && per_cta * kFlatMinCtas <= 227u * 1024u;
+}
+
 // Warp-specialised layout (susnet_ws.cuh); returns false if it does not apply or does not fit.
 bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, WsLayout& L) {
   if (enc.sp_floats <= 0 || (enc.kind != SUS_ENCODE_GLOBAL && enc.kind != SUS_ENCODE_PERSPECTIVE)) return false;
@@ -1111,8 +1213,15 @@ bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool
   return true;
 }
 
-// SUSNET_PATH: "direct" = register/LSU stores, "tma" = every warp stages and stores its own tiles,
-// "ws" (default) = warp-specialised emitter where planes are written, "tma" elsewhere.
+// SUSNET_PATH forces an output path (the GPU tests run every case on all of them): "direct" = register/LSU stores,
+// "tma" = every warp stages and bulk-stores its own tiles, "ws" = warp-specialised emitter where planes are written
+// ("tma" elsewhere), "staged" = byte-staged rows for Flat encodes ("tma" elsewhere).  Unset: "ws" for Global /
+// Perspective, "staged" for Flat.
+bool want_staged_flat() {
+  const char* v = std::getenv("SUSNET_PATH");
+  return !v || std::strcmp(v, "staged") == 0;
+}
+
 bool want_ws() {
   const char* v = std::getenv("SUSNET_PATH");
   return !v || std::strcmp(v, "ws") == 0;
@@ -1316,6 +1425,27 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
         break;
     }
     return after_launch("k_step_ws");
+  }
+  FlatStage FS;
+  if (want_staged_flat() && enc &&
+      make_flat_stage(p.c, p.enc, io->rewards_dtype == SUS_F64 ? 8 : 4, io->next_flat != nullptr, di.max_dyn_smem, FS)) {
+    const size_t smem = (size_t)FS.per_warp * (kThreads / 32);
+    const unsigned gr = grid_for(e->N);
+    switch (e->cfg.variant) {
+      case SUS_VARIANT_BASE:
+        if (int rc = allow_big_smem(k_step_flat<SUS_VARIANT_BASE>, smem)) return rc;
+        k_step_flat<SUS_VARIANT_BASE><<<gr, kThreads, smem, st>>>(p, FS);
+        break;
+      case SUS_VARIANT_TAGGING:
+        if (int rc = allow_big_smem(k_step_flat<SUS_VARIANT_TAGGING>, smem)) return rc;
+        k_step_flat<SUS_VARIANT_TAGGING><<<gr, kThreads, smem, st>>>(p, FS);
+        break;
+      default:
+        if (int rc = allow_big_smem(k_step_flat<SUS_VARIANT_TRAINING_GROUND>, smem)) return rc;
+        k_step_flat<SUS_VARIANT_TRAINING_GROUND><<<gr, kThreads, smem, st>>>(p, FS);
+        break;
+    }
+    return after_launch("k_step_flat");
   }
   if (want_tma() && enc &&
       make_layout(p.c, p.enc, io->rewards_dtype == SUS_F64 ? 8 : 4, io->next_flat != nullptr, di.max_dyn_smem, L)) {

@@ -150,9 +150,32 @@ __device__ __forceinline__ void global_ns_rows(const DevConfig& c, const ObsStat
 
 __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
 
-// One component of a CompositeFeaturizer (component.py); returns the number of floats written.
+// Where a flat row's values go.  FloatRow writes the float32 feature row itself (global memory or a staging row);
+// ByteRow writes one biased byte per value (v + 128) into a row that was PREFILLED with the byte of 0, for the
+// staged-bytes kernel (k_step_flat), which expands the bytes to floats with coalesced 128-bit stores.  Every flat
+// component but the scent one is integer-valued with |v| <= 30, so the byte row is exact.
+struct FloatRow {
+  static constexpr bool kPrefilledZero = false;
+  float* __restrict__ r;
+  __device__ __forceinline__ void put(int p, int v) const { r[p] = (float)v; }
+  __device__ __forceinline__ void putf(int p, float v) const { r[p] = v; }
+};
+constexpr uint32_t kByteRowBias = 128u;
+struct ByteRow {
+  static constexpr bool kPrefilledZero = true;
+  uint8_t* __restrict__ r;
+  __device__ __forceinline__ void put(int p, int v) const { r[p] = (uint8_t)(v + (int)kByteRowBias); }
+  __device__ __forceinline__ void putf(int, float) const {}  // no float-valued component is ever staged as bytes
+};
+// float value of byte k of a word of a ByteRow: the byte becomes the low mantissa bits of 2^23, minus (2^23 + bias)
+__device__ __forceinline__ float byte_row_value(uint32_t w, int k) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)k)) - (8388608.0f + (float)kByteRowBias);
+}
+
+// One component of a CompositeFeaturizer (component.py) written at r[0..n); returns n.
+template <typename Row>
 __device__ __forceinline__ int flat_component(const DevConfig& c, const GridTables& tb, const ObsState& o, int comp,
-                                              float* __restrict__ r) {
+                                              const Row& r) {
   const int A = c.A, J = c.J;
   const uint32_t b0 = get_byte(o.pos, 0);  // "imposter is agent 0" (component.py:262,289,355,440,467)
   const int ix = (int)code_x(b0), iy = (int)code_y(b0);
@@ -162,18 +185,24 @@ __device__ __forceinline__ int flat_component(const DevConfig& c, const GridTabl
       for (int i = 0; i < A; ++i) {
         const uint32_t b = get_byte(o.pos, i);
         const bool al = (o.alive >> i) & 1u;
-        for (int q = 0; q < 9; ++q) r[p++] = (al && code_x(b) == (uint32_t)q) ? 1.0f : 0.0f;
-        for (int q = 0; q < 9; ++q) r[p++] = (al && code_y(b) == (uint32_t)q) ? 1.0f : 0.0f;
+        if (Row::kPrefilledZero) {  // only the (at most two) ones of an alive agent
+          if (al && code_x(b) < 9u) r.put(p + (int)code_x(b), 1);
+          if (al && code_y(b) < 9u) r.put(p + 9 + (int)code_y(b), 1);
+          p += 18;
+        } else {
+          for (int q = 0; q < 9; ++q) r.put(p++, (al && code_x(b) == (uint32_t)q) ? 1 : 0);
+          for (int q = 0; q < 9; ++q) r.put(p++, (al && code_y(b) == (uint32_t)q) ? 1 : 0);
+        }
       }
       break;
     case SUS_FC_COORDS:  // component.py:389-399 (dead agents included)
       for (int i = 0; i < A; ++i) {
         const uint32_t b = get_byte(o.pos, i);
-        r[p++] = (float)code_x(b); r[p++] = (float)code_y(b);
+        r.put(p++, (int)code_x(b)); r.put(p++, (int)code_y(b));
       }
       break;
     case SUS_FC_ALIVE_CREW:  // component.py:411-421
-      for (int i = 1; i < A; ++i) r[p++] = (float)((o.alive >> i) & 1u);
+      for (int i = 1; i < A; ++i) r.put(p++, (int)((o.alive >> i) & 1u));
       break;
     case SUS_FC_CLOSEST_CREW: {  // component.py:460-478: default distance 18, first argmin
       int best = 0, best_d = 1 << 20;
@@ -182,28 +211,28 @@ __device__ __forceinline__ int flat_component(const DevConfig& c, const GridTabl
         const int d = ((o.alive >> i) & 1u) ? iabs(ix - (int)code_x(b)) + iabs(iy - (int)code_y(b)) : 18;
         if (d < best_d) { best_d = d; best = i - 1; }
       }
-      for (int i = 0; i < A - 1; ++i) r[p++] = i == best ? 1.0f : 0.0f;
+      for (int i = 0; i < A - 1; ++i) r.put(p++, i == best ? 1 : 0);
     } break;
     case SUS_FC_L1_CREW:  // component.py:433-448
       for (int i = 1; i < A; ++i) {
         const uint32_t b = get_byte(o.pos, i);
-        r[p++] = ((o.alive >> i) & 1u) ? (float)(iabs(ix - (int)code_x(b)) + iabs(iy - (int)code_y(b))) : -1.0f;
+        r.put(p++, ((o.alive >> i) & 1u) ? iabs(ix - (int)code_x(b)) + iabs(iy - (int)code_y(b)) : -1);
       }
       break;
     case SUS_FC_DIST_TO_IMPOSTER: {  // component.py:255-273: alive others compacted, trailing zeros
       const int n = 2 * (A - 1);
       for (int i = 1; i < A; ++i) {
         const uint32_t b = get_byte(o.pos, i);
-        if ((o.alive >> i) & 1u) { r[p++] = (float)(ix - (int)code_x(b)); r[p++] = (float)(iy - (int)code_y(b)); }
+        if ((o.alive >> i) & 1u) { r.put(p++, ix - (int)code_x(b)); r.put(p++, iy - (int)code_y(b)); }
       }
-      while (p < n) r[p++] = 0.0f;
+      while (p < n) r.put(p++, 0);
     } break;
     case SUS_FC_WALLS:  // component.py:286-296: 3x3 patch of the zero-padded grid around agent 0
       for (int dx = -1; dx <= 1; ++dx)
         for (int dy = -1; dy <= 1; ++dy) {
           const uint32_t nb = ((uint32_t)(ix + dx) << 4 | ((uint32_t)(iy + dy) & 15u)) & 0xffu;
           const bool in = (uint32_t)(ix + dx) <= 8u && (uint32_t)(iy + dy) <= 8u;
-          r[p++] = (in && ((tb.valid_bits[nb >> 5] >> (nb & 31u)) & 1u)) ? 1.0f : 0.0f;
+          r.put(p++, (in && ((tb.valid_bits[nb >> 5] >> (nb & 31u)) & 1u)) ? 1 : 0);
         }
       break;
     case SUS_FC_ROOMS: {  // component.py:308-329, ROOM_MASKS component.py:8-17
@@ -218,7 +247,7 @@ __device__ __forceinline__ int flat_component(const DevConfig& c, const GridTabl
         for (int q = 0; q < 8; ++q) cnt[q] += q == at ? 1 : 0;
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) r[p++] = (float)cnt[q];
+      for (int q = 0; q < 8; ++q) r.put(p++, cnt[q]);
     } break;
     case SUS_FC_SCENT: {  // component.py:344-375: float32 accumulation of (9 - d) / 9 computed in double
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -229,22 +258,29 @@ __device__ __forceinline__ int flat_component(const DevConfig& c, const GridTabl
         if (xs > 0) s0 += (float)xs; else s1 += (float)xs;
         if (ys > 0) s2 += (float)ys; else s3 += (float)ys;
       }
-      r[p++] = s0; r[p++] = s1; r[p++] = s2; r[p++] = s3;
+      r.putf(p++, s0); r.putf(p++, s1); r.putf(p++, s2); r.putf(p++, s3);
     } break;
     case SUS_FC_STATE_ALIVE:  // StateFieldFeaturizer: component.py:210-214
-      for (int i = 0; i < A; ++i) r[p++] = (float)((o.alive >> i) & 1u);
+      for (int i = 0; i < A; ++i) r.put(p++, (int)((o.alive >> i) & 1u));
       break;
     case SUS_FC_STATE_JOB_STATUS:
-      for (int j = 0; j < J; ++j) r[p++] = (float)((o.jobdone >> j) & 1u);
+      for (int j = 0; j < J; ++j) r.put(p++, (int)((o.jobdone >> j) & 1u));
       break;
     case SUS_FC_STATE_USED_TAGS:
-      for (int i = 0; i < A; ++i) r[p++] = (float)((o.used >> i) & 1u);
+      for (int i = 0; i < A; ++i) r.put(p++, (int)((o.used >> i) & 1u));
       break;
     case SUS_FC_STATE_TAG_COUNTS:
-      for (int i = 0; i < A; ++i) r[p++] = (float)((o.tagcnt >> (4 * i)) & 15u);
+      for (int i = 0; i < A; ++i) r.put(p++, (int)((o.tagcnt >> (4 * i)) & 15u));
       break;
   }
   return p;
+}
+
+// all components of a flat row, back to back
+template <typename RowT, typename Elem>
+__device__ __forceinline__ void flat_row(const DevConfig& c, const DevEncode& enc, const GridTables& tb, const ObsState& o,
+                                         Elem* __restrict__ row) {
+  for (int q = 0; q < enc.n_components; ++q) row += flat_component(c, tb, o, enc.components[q], RowT{row});
 }
 
 // Encode the 32 items a warp owns (item = item0 + lane; `cnt` of them exist, `have` says whether this
@@ -275,10 +311,7 @@ __device__ __forceinline__ void warp_encode(const DevConfig& c, const DevEncode&
       }
     }
   } else if (enc.kind == SUS_ENCODE_FLAT) {
-    if (have) {
-      float* r = non_spatial + item * enc.ns_floats;
-      for (int q = 0; q < enc.n_components; ++q) r += flat_component(c, tb, o, enc.components[q], r);
-    }
+    if (have) flat_row<FloatRow>(c, enc, tb, o, non_spatial + item * enc.ns_floats);
   }
 }
 

@@ -143,8 +143,7 @@ __device__ __forceinline__ void warp_encode_tma(const DevConfig& c, const DevEnc
     } else if (enc.kind == SUS_ENCODE_PERSPECTIVE) {
       for (int k = 0; k < A; ++k) persp_ns_row(c, o, k, ns + (k * 32 + lane) * F);
     } else {
-      float* r = ns + lane * F;
-      for (int q = 0; q < enc.n_components; ++q) r += flat_component(c, tb, o, enc.components[q], r);
+      flat_row<FloatRow>(c, enc, tb, o, ns + lane * F);
     }
   }
   fence_proxy_async_smem();

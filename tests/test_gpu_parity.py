@@ -13,10 +13,11 @@ from tests.util import CASES, case_of, flat_featurizer, golden_files, load, make
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["ws", "tma", "direct"], autouse=True)
+@pytest.fixture(params=["ws", "tma", "direct", "staged"], autouse=True)
 def store_path(request, monkeypatch):
     """Every GPU test runs on all output paths of the kernels: warp-specialised emitter + TMA bulk stores (default where
-    planes are written), per-warp staging + TMA bulk stores, and direct register stores (the fallback)."""
+    planes are written), per-warp staging + TMA bulk stores, direct register stores (the fallback), and byte-staged
+    rows expanded with coalesced stores (default for Flat encodes; other encodes take the per-warp TMA path there)."""
     monkeypatch.setenv("SUSNET_PATH", request.param)
     return request.param
 
