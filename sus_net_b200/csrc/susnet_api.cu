@@ -8,9 +8,11 @@
 //   K1+K2 k_step_ws<V>         the step FUSED with the observation encode of the state the next action is taken
 //                              from, warp-specialised: compute warps + one TMA emitter warp per persistent CTA
 //                              (Global / Perspective; the headline kernel)
-//         k_step_tma<V, true>  same fusion, every warp stages and bulk-stores its own tiles (Flat encodes)
+//         k_step_flat<V>       same fusion for Flat encodes: one thread per env at 32 warps / SM, rows staged as one byte
+//                              per value in shared memory and expanded with lane-contiguous 128-bit stores
+//         k_step_tma<V, true>  same fusion, every warp stages and bulk-stores its own tiles (SUSNET_PATH=tma)
 //         k_step<V, true>      same fusion with direct register stores (fallback, SUSNET_PATH=direct)
-//   K2    k_encode_ws / k_encode_tma / k_encode_env / k_encode_rows<T>
+//   K2    k_encode_ws / k_encode_flat / k_encode_tma / k_encode_env / k_encode_rows<T>
 //                              featurizers on live env state / on (B*T, S) flattened rows (= featurizer.fit)
 //   K3    k_sample_actions     role-aware uniform random actions
 //         k_rollout<V>         n random-policy steps per launch with the env state in registers
@@ -362,6 +364,29 @@ __device__ __forceinline__ void warp_copy_words(uint32_t* __restrict__ g, const 
   for (int i = done + lane; i < n_words; i += 32) g[i] = s[i];
 }
 
+// Expand a warp's staged byte rows to `n` floats at `out`: word i of the block holds floats [4i, 4i + 4).  Lane-contiguous
+// 128-bit stores when `out` is 16-byte aligned, scalar stores otherwise and over a ragged tail.  All 32 lanes, after the
+// rows are complete (__syncwarp / any warp collective).
+__device__ __forceinline__ void warp_expand_byte_rows(float* __restrict__ out, const uint32_t* __restrict__ w, int n, int lane) {
+  int done = 0;
+  if (((uint32_t)reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const int n4 = n >> 2;
+    constexpr int kBatch = 8;  // words loaded before the first is expanded: the LDS latency is paid once per batch
+    for (int i0 = lane; i0 < n4; i0 += 32 * kBatch) {
+      uint32_t x[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) x[b] = i0 + 32 * b < n4 ? w[i0 + 32 * b] : 0u;
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b)
+        if (i0 + 32 * b < n4)
+          reinterpret_cast<float4*>(out)[i0 + 32 * b] = make_float4(byte_row_value(x[b], 0), byte_row_value(x[b], 1),
+                                                                    byte_row_value(x[b], 2), byte_row_value(x[b], 3));
+    }
+    done = n4 << 2;
+  }
+  for (int i = done + lane; i < n; i += 32) out[i] = byte_row_value(w[i >> 2], i & 3);
+}
+
 // K1+K2 for FLAT encodes (the reference's training recipes: one-hot positions + crew flags, component.py): one thread
 // per env at high occupancy.  A flat row is F mostly-zero small integers, so each warp stages its 32 rows as ONE BYTE
 // per value (prefilled with the byte of 0; the one-hot segments only set their ones), then all lanes expand the
@@ -370,17 +395,19 @@ __device__ __forceinline__ void warp_copy_words(uint32_t* __restrict__ g, const 
 // (measured: time ~ 0.06 ms + 1.0 ms / warps per SM at 1 Mi envs), so occupancy is what pays.  Rewards and the replay
 // row are staged as words and leave the same way.
 constexpr int kFlatMinCtas = 4;
-template <int VARIANT>
+template <int VARIANT, int TA = 0, int TJ = 0>
 __global__ void __launch_bounds__(kThreads, kFlatMinCtas) k_step_flat(const __grid_constant__ StepParams p,
                                                                        const __grid_constant__ FlatStage L) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ GridTables tb;
-  stage_tables(p.c, tb);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int A = p.c.A, S = p.c.S, F = p.enc.ns_floats;
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x, e0 = e - lane;
-  if (e0 >= p.N) return;  // whole warp
   const bool have = e < p.N;
+  StepInput in;
+  load_input(p, e, have, in);  // in flight while the tables and the row prefill are set up
+  stage_tables(p.c, tb);
+  if (e0 >= p.N) return;  // whole warp
   const int cnt = p.N - e0 < 32 ? (int)(p.N - e0) : 32;
   uint8_t* blk = dyn_smem + (size_t)warp * L.per_warp;
   {
@@ -393,9 +420,7 @@ __global__ void __launch_bounds__(kThreads, kFlatMinCtas) k_step_flat(const __gr
   bool stepped, finished;
   EnvState s = {};
   StepResult r = {};
-  StepInput in;
-  load_input(p, e, have, in);
-  step_one<VARIANT>(p, tb, e, have, in, p.rewards ? rew + lane * A * rew_elem : nullptr, p.next_flat ? nf + lane * S : nullptr,
+  step_one<VARIANT, TA, TJ>(p, tb, e, have, in, p.rewards ? rew + lane * A * rew_elem : nullptr, p.next_flat ? nf + lane * S : nullptr,
                     s, r, stepped, finished);
   finish_one(p, tb, e, lane, s, r, stepped, finished);
   __syncwarp();  // the prefill is complete before any lane sets bytes in its row
@@ -415,22 +440,7 @@ __global__ void __launch_bounds__(kThreads, kFlatMinCtas) k_step_flat(const __gr
     if (p.next_flat)
       for (int i = 0; i < S; ++i) p.next_flat[e * S + i] = nf[lane * S + i];
   }
-  // expand the byte rows: word i of the block holds floats [4i, 4i + 4) of the warp's cnt x F output floats
-  float* out = p.non_spatial + e0 * F;
-  const int n = cnt * F;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(blk);
-  int done = 0;
-  if (((uint32_t)reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
-    const int n4 = n >> 2;
-#pragma unroll 4
-    for (int i = lane; i < n4; i += 32) {
-      const uint32_t x = w[i];
-      reinterpret_cast<float4*>(out)[i] =
-          make_float4(byte_row_value(x, 0), byte_row_value(x, 1), byte_row_value(x, 2), byte_row_value(x, 3));
-    }
-    done = n4 << 2;
-  }
-  for (int i = done + lane; i < n; i += 32) out[i] = byte_row_value(w[i >> 2], i & 3);
+  warp_expand_byte_rows(p.non_spatial + e0 * F, reinterpret_cast<const uint32_t*>(blk), cnt * F, lane);
 }
 
 // Random-policy rollout: every env advances `n_steps` steps inside ONE launch with its state in registers
@@ -854,6 +864,37 @@ __global__ void __launch_bounds__(kThreads) k_encode_rows(const __grid_constant_
   if (have) o = parse_row<T>(p.c, static_cast<const T*>(p.rows) + e * p.c.S);
   const int64_t rem = p.n_items - e0;
   warp_encode(p.c, p.enc, tb, o, e0, rem < 32 ? (int)(rem < 0 ? 0 : rem) : 32, have, p.n_items, p.spatial, p.non_spatial);
+}
+
+// K2 for FLAT encodes, byte-staged like k_step_flat: live env state (FROM_ROWS = false) or (B*T, S) rows.
+template <typename T, bool FROM_ROWS>
+__global__ void __launch_bounds__(kThreads, kFlatMinCtas) k_encode_flat(const __grid_constant__ EncodeParams p,
+                                                                         const __grid_constant__ FlatStage L) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ GridTables tb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, F = p.enc.ns_floats;
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x, e0 = e - lane;
+  const bool have = e < p.n_items;
+  ObsState o = {};
+  if (have) {
+    if (FROM_ROWS) {
+      o = parse_row<T>(p.c, static_cast<const T*>(p.rows) + e * p.c.S);
+    } else {
+      EnvState s;
+      load_state(p.st, e, s);
+      o = obs_of(s);
+    }
+  }
+  stage_tables(p.c, tb);
+  if (e0 >= p.n_items) return;  // whole warp
+  const int cnt = p.n_items - e0 < 32 ? (int)(p.n_items - e0) : 32;
+  uint8_t* blk = dyn_smem + (size_t)warp * L.per_warp;
+  const uint32_t z = kByteRowBias * 0x01010101u;
+  for (int i = lane; i < (L.row_bytes >> 4); i += 32) reinterpret_cast<uint4*>(blk)[i] = make_uint4(z, z, z, z);
+  __syncwarp();
+  if (have) flat_row<ByteRow>(p.c, p.enc, tb, o, blk + lane * F);
+  __syncwarp();
+  warp_expand_byte_rows(p.non_spatial + e0 * F, reinterpret_cast<const uint32_t*>(blk), cnt * F, lane);
 }
 
 // K2, TMA path (see k_step_tma): persistent CTAs, features staged in shared memory, bulk stores.
@@ -1441,8 +1482,13 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
         k_step_flat<SUS_VARIANT_TAGGING><<<gr, kThreads, smem, st>>>(p, FS);
         break;
       default:
-        if (int rc = allow_big_smem(k_step_flat<SUS_VARIANT_TRAINING_GROUND>, smem)) return rc;
-        k_step_flat<SUS_VARIANT_TRAINING_GROUND><<<gr, kThreads, smem, st>>>(p, FS);
+        if (p.c.A == 5 && p.c.J == 0) {  // the reference's training shape: compile-time agent / job counts
+          if (int rc = allow_big_smem(k_step_flat<SUS_VARIANT_TRAINING_GROUND, 5, 0>, smem)) return rc;
+          k_step_flat<SUS_VARIANT_TRAINING_GROUND, 5, 0><<<gr, kThreads, smem, st>>>(p, FS);
+        } else {
+          if (int rc = allow_big_smem(k_step_flat<SUS_VARIANT_TRAINING_GROUND>, smem)) return rc;
+          k_step_flat<SUS_VARIANT_TRAINING_GROUND><<<gr, kThreads, smem, st>>>(p, FS);
+        }
         break;
     }
     return after_launch("k_step_flat");
@@ -1621,6 +1667,13 @@ int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float
     k_encode_ws<float, false><<<ws_grid(e->N, W, di.sms), (W.compute_warps + 1) * 32, W.total_bytes, (cudaStream_t)stream>>>(p, W);
     return after_launch("k_encode_ws");
   }
+  FlatStage FS;
+  if (want_staged_flat() && make_flat_stage(p.c, p.enc, 0, false, di.max_dyn_smem, FS)) {
+    const size_t smem = (size_t)FS.per_warp * (kThreads / 32);
+    if (int rc = allow_big_smem(k_encode_flat<float, false>, smem)) return rc;
+    k_encode_flat<float, false><<<grid_for(e->N), kThreads, smem, (cudaStream_t)stream>>>(p, FS);
+    return after_launch("k_encode_flat");
+  }
   TileLayout L;
   if (want_tma() && make_layout(p.c, p.enc, 0, false, di.max_dyn_smem, L)) {
     const size_t smem = (size_t)L.per_warp * L.warps;
@@ -1668,6 +1721,22 @@ int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const 
       k_encode_ws<long long, true><<<gr, threads, W.total_bytes, st>>>(p, W);
     }
     return after_launch("k_encode_ws");
+  }
+  FlatStage FS;
+  if (want_staged_flat() && make_flat_stage(p.c, p.enc, 0, false, di.max_dyn_smem, FS)) {
+    const size_t smem = (size_t)FS.per_warp * (kThreads / 32);
+    const unsigned gr = grid_for(n_items);
+    if (dtype == SUS_F32) {
+      if (int rc = allow_big_smem(k_encode_flat<float, true>, smem)) return rc;
+      k_encode_flat<float, true><<<gr, kThreads, smem, st>>>(p, FS);
+    } else if (dtype == SUS_F64) {
+      if (int rc = allow_big_smem(k_encode_flat<double, true>, smem)) return rc;
+      k_encode_flat<double, true><<<gr, kThreads, smem, st>>>(p, FS);
+    } else {
+      if (int rc = allow_big_smem(k_encode_flat<long long, true>, smem)) return rc;
+      k_encode_flat<long long, true><<<gr, kThreads, smem, st>>>(p, FS);
+    }
+    return after_launch("k_encode_flat");
   }
   TileLayout L;
   if (want_tma() && make_layout(p.c, p.enc, 0, false, di.max_dyn_smem, L)) {
