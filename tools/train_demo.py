@@ -48,9 +48,8 @@ class RandomQ(nn.Module):
 
     def forward(self, spatial_x, non_spatial_x):
         b = spatial_x.size(0)
-        out = torch.zeros(b, self.n, device=spatial_x.device)
-        out[torch.arange(b, device=out.device), torch.randint(0, self.n, (b,), device=out.device)] = 1
-        return out
+        pick = torch.randint(0, self.n, (b, 1), device=spatial_x.device)
+        return torch.zeros(b, self.n, device=spatial_x.device).scatter_(1, pick, 1.0)  # (no host scalar: `out[i, j] = 1` costs a pageable H2D copy per call)
 
     def create_copy(self):
         return RandomQ(self.n)
@@ -61,7 +60,9 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=131072)
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core GEMMs in the Q-network")
     a = ap.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = a.tf32
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -92,6 +93,7 @@ def main():
         m = S.EpisodicMetricHandler(); m.update_from_stats(stats)
         print(json.dumps({"config": "cfg5 batched DQN loop (acting + step + replay push + train every 5)",
                           "n_gpus": world, "envs_per_gpu": N, "iterations": a.iters, "wall_s": dt,
+                          "tf32_q_network": a.tf32,
                           "env_steps_per_s_in_training_loop": world * N * a.iters / dt,
                           "train_steps": len(losses), "last_losses": losses[-1],
                           "episodes": int(stats[0]), "imposter_win_rate": float(stats[2]) / max(int(stats[0]), 1)}))
