@@ -32,13 +32,24 @@ CASES = {
 
 # featurizer coverage per case: which model-ready featurizers are defined for it
 GLOBAL_CASES = ["cfg4_base_1v4", "base_2v3_j3", "base_fixed_order_tsr", "base_1v7_j8_nowall", "itg_1v3_jobs_shuffle"]
+# sets with "scent" (the one float-valued component) take the float-row paths; the scent-free ones exercise the byte-staged
+# rows of k_step_flat / k_encode_flat on every integer-valued component (negative values, tagging fields, two one-hot
+# segments in one row)
 FLAT_COMPONENT_SETS = {
     "cfg4alt_itg_1v4": [["onehot_pos", "alive_crew", "closest_crew"],
-                        ["coords", "l1_crew", "dist_to_imposter", "walls", "rooms", "scent", "state_alive"]],
+                        ["coords", "l1_crew", "dist_to_imposter", "walls", "rooms", "scent", "state_alive"],
+                        ["coords", "l1_crew", "dist_to_imposter", "walls", "rooms", "state_alive", "onehot_pos"]],
     "cfg2_itg_1v1_wall": [["onehot_pos"], ["coords"]],
     "cfg1_itg_1v1_nowall": [["onehot_pos"], ["walls", "rooms"]],
     "cfg4_base_1v4": [["onehot_pos", "state_alive", "state_job_status", "walls", "rooms", "l1_crew", "closest_crew",
-                       "dist_to_imposter", "scent", "coords", "alive_crew"]],
+                       "dist_to_imposter", "scent", "coords", "alive_crew"],
+                      ["onehot_pos", "state_alive", "state_job_status", "walls", "rooms", "l1_crew", "closest_crew",
+                       "dist_to_imposter", "coords", "alive_crew", "onehot_pos"]],
+}
+# CUDA vs oracle only: the reference's own featurizers raise on the tagging env (its state_fields map is inconsistent,
+# SURVEY.md App. C-7), so there is nothing to pin these against
+FLAT_COMPONENT_SETS_TAGGING = {
+    "cfg3_tagging_1v2": [["state_used_tags", "state_tag_counts", "onehot_pos", "state_job_status", "dist_to_imposter"]],
 }
 
 

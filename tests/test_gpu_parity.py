@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import oracle
-from tests.cases import FLAT_COMPONENT_SETS, GLOBAL_CASES
+from tests.cases import FLAT_COMPONENT_SETS, FLAT_COMPONENT_SETS_TAGGING, GLOBAL_CASES
 from tests.util import CASES, case_of, flat_featurizer, golden_files, load, make_cuda_env, reward_bits
 
 pytestmark = pytest.mark.gpu
@@ -133,7 +133,7 @@ def test_cuda_matches_oracle_at_scale(cuda_lib, name):
     del acts
 
 
-@pytest.mark.parametrize("name", GLOBAL_CASES + list(FLAT_COMPONENT_SETS))
+@pytest.mark.parametrize("name", GLOBAL_CASES + list(FLAT_COMPONENT_SETS) + list(FLAT_COMPONENT_SETS_TAGGING))
 def test_fused_step_encode_matches_oracle(cuda_lib, name):
     """The fused K1+K2 launch must write the features of the state the next action is taken from (post auto-reset)."""
     import sus_net_b200 as S
@@ -146,7 +146,7 @@ def test_fused_step_encode_matches_oracle(cuda_lib, name):
     feats = []
     if name in GLOBAL_CASES:
         feats += [("global", S.GlobalFeaturizer(env)), ("perspective", S.PerspectiveFeaturizer(env))]
-    for comps in FLAT_COMPONENT_SETS.get(name, []):
+    for comps in FLAT_COMPONENT_SETS.get(name, []) + FLAT_COMPONENT_SETS_TAGGING.get(name, []):
         feats.append((comps, flat_featurizer(env, comps)))
     for t in range(T):
         kind, f = feats[t % len(feats)]
