@@ -426,6 +426,51 @@ def test_unaligned_output_pointers_through_the_c_abi(cuda_lib):
                 assert (cpu(ns_raw[:off]) == -7).all() and (cpu(ns_raw[off + ns_n:]) == -7).all()
 
 
+def test_flat_rows_unaligned_and_ragged_through_the_c_abi(cuda_lib):
+    """Flat rows with an odd float count (F = 39) on ragged env counts, written to 4-byte-aligned tensors by the standalone
+    encode AND by the fused step (rewards / replay row / features all unaligned): the staged paths must fall back to scalar
+    stores where a block is not 16-byte aligned or a multiple of 16 bytes, and touch nothing outside the tensors."""
+    import ctypes as C
+
+    from sus_net_b200 import _lib as L
+
+    cfg = CASES["cfg4alt_itg_1v4"]
+    comps = ["alive_crew", "l1_crew", "dist_to_imposter", "walls", "closest_crew", "coords"]  # 4 + 4 + 8 + 9 + 4 + 10
+    ids = (C.c_int32 * L.MAX_FLAT_COMPONENTS)(*[oracle.FLAT_COMPONENTS[c] for c in comps])
+    for N in (1003, 37, 5):
+        env = make_cuda_env(cfg, N, seed=3)
+        orc = oracle.OracleEnv(cfg, N, seed=3)
+        env.reset(); orc.reset()
+        spec = L.SusEncodeSpec(kind=L.ENCODE_FLAT, n_components=len(comps), components=ids)
+        sh = L.SusEncodeShape()
+        L.check(env.lib.sus_encode_shape(C.byref(env._cfg), C.byref(spec), C.byref(sh)))
+        F, A, S = sh.non_spatial_floats, env.n_agents, env.flattened_state_size
+        assert F == 39
+        for off in (0, 1, 2, 3):
+            ns_raw = torch.full((N * F + 8,), -7.0, device=env.device)
+            ns = ns_raw[off:off + N * F]
+            L.check(env.lib.sus_env_encode(env._h, C.byref(spec), None, C.c_void_p(ns.data_ptr()), env._stream()))
+            assert np.array_equal(cpu(ns).reshape(N, F), oracle.encode_flat(cfg, comps, orc.flat_states()))
+            assert (cpu(ns_raw[:off]) == -7).all() and (cpu(ns_raw[off + N * F:]) == -7).all()
+            # fused step: random policy in the kernel, every dense output 4-byte aligned only
+            rew_raw = torch.full((N * A + 8,), -7.0, device=env.device)
+            nf_raw = torch.full((N * S + 8,), -7.0, device=env.device)
+            ns_raw.fill_(-7.0)
+            rew, nf = rew_raw[off:off + N * A], nf_raw[off:off + N * S]
+            done, trunc = torch.zeros(N, dtype=torch.uint8, device=env.device), torch.zeros(N, dtype=torch.uint8, device=env.device)
+            io = L.SusStepIO(actions=None, actions_dtype=L.I32, rewards=rew.data_ptr(), rewards_dtype=L.F32,
+                             done=done.data_ptr(), truncated=trunc.data_ptr(), next_flat=nf.data_ptr(),
+                             encode=C.pointer(spec), non_spatial=ns.data_ptr())
+            L.check(env.lib.sus_env_step(env._h, C.byref(io), env._stream()))
+            o = orc.step(None)
+            assert np.array_equal(cpu(rew).reshape(N, A), o["rewards"].astype(np.float32))
+            assert np.array_equal(cpu(nf).reshape(N, S).astype(np.int64), o["next_flat"])
+            assert np.array_equal(cpu(done), o["done"]) and np.array_equal(cpu(trunc), o["trunc"])
+            assert np.array_equal(cpu(ns).reshape(N, F), oracle.encode_flat(cfg, comps, orc.flat_states()))
+            for raw, n in ((rew_raw, N * A), (nf_raw, N * S), (ns_raw, N * F)):
+                assert (cpu(raw[:off]) == -7).all() and (cpu(raw[off + n:]) == -7).all()
+
+
 @pytest.mark.parametrize("name", ["cfg4_base_1v4", "tagging_2v5_short", "base_fixed_order_tsr"])
 def test_tracked_returns_match_oracle(cuda_lib, name):
     """train()'s running returns G = r + gamma * G per agent (train.py:386) kept on the device: per-episode means summed
