@@ -5,7 +5,9 @@ random policy, compared with the oracle on the same Philox draws:
   * at the end: rewards / dones of the last step identical, the feature tensors of a 65 536-env slice identical, and for
     ALL envs the size-independent property "ones in the planes == alive agents + jobs" and a checksum of the non-spatial
     views against the oracle's.
-    python tools/soak_parity.py [--envs 1048576] [--steps 1000] [--check-every 100]
+`--config flat` runs the cfg4-alt shape instead (ImposterTrainingGround 1v4, walled, Flat-98 features through the
+byte-staged k_step_flat) and compares the feature rows of ALL envs at every checkpoint.
+    python tools/soak_parity.py [--envs 1048576] [--steps 1000] [--check-every 100] [--config global|flat]
 """
 import argparse
 import json
@@ -26,8 +28,11 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 20)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--check-every", type=int, default=100)
+    ap.add_argument("--config", choices=["global", "flat"], default="global")
     a = ap.parse_args()
     N, T = a.envs, a.steps
+    if a.config == "flat":
+        return soak_flat(N, T, a.check_every)
     cfg = oracle.default_config("base", n_crew=4, n_jobs=5)
     env = S.BatchedFourRoomEnv(1, 4, 5, num_envs=N, seed=99, device="cuda:0")
     feat = S.GlobalFeaturizer(env)
@@ -64,6 +69,36 @@ def main():
     print(json.dumps({"envs": N, "steps": T, "env_steps": N * T, "full_state_comparisons": checks,
                       "finished_trajectories": stats["episodes"], "stats": stats, "wall_s": round(time.time() - t0, 1),
                       "result": "identical"}))
+
+
+def soak_flat(N, T, check_every):
+    from tests.cases import CASES
+    from tests.util import flat_featurizer, make_cuda_env
+
+    cfg = CASES["cfg4alt_itg_1v4"]
+    comps = ["onehot_pos", "alive_crew", "closest_crew"]
+    env = make_cuda_env(cfg, N, seed=99)
+    feat = flat_featurizer(env, comps)
+    orc = oracle.OracleEnv(cfg, N, seed=99)
+    oracle.set_threads(os.cpu_count() or 1)
+    assert np.array_equal(env.reset()[0].cpu().numpy().astype(np.int64), orc.reset())
+    t0, out, checks = time.time(), None, 0
+    for t in range(1, T + 1):
+        nf, r, d, tr, _ = env.step(None, featurizer=feat)
+        out = orc.step(None, want_flat=False, want_metrics=False, out=out)
+        if t % check_every == 0 or t == T:
+            cur = orc.flat_states()
+            assert np.array_equal(env.flat_states(torch.int64).cpu().numpy(), cur), f"states differ at step {t}"
+            assert np.array_equal(env.episode_stats().cpu().numpy(), orc.stats()), f"episode stats differ at step {t}"
+            assert np.array_equal(r.cpu().numpy(), out["rewards"].astype(np.float32)), f"rewards differ at step {t}"
+            assert np.array_equal(d.cpu().numpy(), out["done"] != 0), f"dones differ at step {t}"
+            got = feat.generate_featurized_states()[0][1].detach()[:, 0].cpu().numpy()
+            assert np.array_equal(got.view(np.int32), oracle.encode_flat(cfg, comps, cur).view(np.int32)), f"features differ at step {t}"
+            checks += 1
+    stats = dict(zip(S.STAT_KEYS, [int(x) for x in orc.stats()]))
+    print(json.dumps({"config": "cfg4-alt ITG 1v4 walled + Flat-98 (k_step_flat)", "envs": N, "steps": T, "env_steps": N * T,
+                      "full_state_and_feature_comparisons": checks, "finished_trajectories": stats["episodes"], "stats": stats,
+                      "wall_s": round(time.time() - t0, 1), "result": "identical"}))
 
 
 if __name__ == "__main__":
