@@ -88,6 +88,7 @@ struct StepParams {
   double* ret_sums;  // [2] sums over finished episodes of mean imposter / mean crew return (train.py:421-424)
   double gamma;
   uint64_t tick;
+  const uint64_t* tick_dev;  // device-resident tick (sus_env_device_ticks) or nullptr: use `tick`
   int64_t N;
   int32_t actions_dtype, rewards_dtype;
 };
@@ -98,6 +99,7 @@ struct ResetParams {
   const uint8_t* mask;
   const uint32_t* inj_reset;
   uint64_t tick;
+  const uint64_t* tick_dev;
   int64_t N;
 };
 
@@ -133,10 +135,18 @@ struct ActParams {
   int32_t* out;
   const uint32_t* inj_act;
   uint64_t tick;
+  const uint64_t* tick_dev;
   int64_t N;
 };
 
 // ------------------------------------------------------------------------------------------ kernels
+// The launch tick of a Philox stream: a kernel parameter, or -- with device-resident ticks, which is what makes a
+// launch replayable inside a CUDA graph -- the counter in device memory that k_advance_tick bumps after every launch.
+template <typename P>
+__device__ __forceinline__ uint64_t launch_tick(const P& p) { return p.tick_dev ? __ldg(p.tick_dev) : p.tick; }
+
+__global__ void k_advance_tick(uint64_t* tick, uint64_t n) { *tick += n; }
+
 __device__ __forceinline__ uint32_t role_actions_rt(const DevConfig& c, uint32_t is_imp) {
   if (c.variant == SUS_VARIANT_TRAINING_GROUND) return 5u + is_imp;
   const uint32_t base = 6u + is_imp;
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ Rese
   if (p.mask && !p.mask[e]) return;
   EnvState s;
   WordStream ws;
-  ws.init(p.c, p.inj_reset ? p.inj_reset + e * (p.c.nI + p.c.A + p.c.J) : nullptr, (uint32_t)e, p.tick, P_RESET);
+  ws.init(p.c, p.inj_reset ? p.inj_reset + e * (p.c.nI + p.c.A + p.c.J) : nullptr, (uint32_t)e, launch_tick(p), P_RESET);
   reset_env(p.c, tb, s, ws);
   store_state(p.st, e, s, true);
 }
@@ -228,7 +238,7 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
   uint64_t acts = pack_actions(in, A, ok);
   if (p.actions == nullptr) {  // fused random policy == env.step(env.sample_actions()), base.py:326-330
     WordStream wa;
-    wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, p.tick, P_ACT_FUSED);
+    wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, launch_tick(p), P_ACT_FUSED);
     for (int i = 0; i < A; ++i)
       acts |= (uint64_t)bounded(wa.word(i), n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) << (8 * i);
   } else {
@@ -243,7 +253,7 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
     return;
   }
   WordStream ws;
-  ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, p.tick, P_STEP);
+  ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, launch_tick(p), P_STEP);
   step_env<VARIANT, TA, TJ>(c, tb, s, acts, ws, r);
   stepped = true;
   finished = r.done || r.trunc;
@@ -312,7 +322,7 @@ __device__ __forceinline__ void finish_one(const StepParams& p, const GridTables
   if (stepped) {
     if (finished && c.auto_reset) {  // SURVEY.md A.7; train.py:419-445 does this on the host
       WordStream wr;
-      wr.init(c, p.inj_reset ? p.inj_reset + e * (c.nI + c.A + c.J) : nullptr, (uint32_t)e, p.tick, P_AUTORESET);
+      wr.init(c, p.inj_reset ? p.inj_reset + e * (c.nI + c.A + c.J) : nullptr, (uint32_t)e, launch_tick(p), P_AUTORESET);
       reset_env(c, tb, s, wr);
       store_state(p.st, e, s, true);
     } else {
@@ -453,6 +463,7 @@ struct RolloutParams {
   unsigned long long* stats;
   double* reward_sums;  // [N][A] or nullptr: sum over the rollout of each agent index's rewards
   uint64_t tick0;
+  const uint64_t* tick_dev;
   int64_t N;
   int32_t n_steps;
 };
@@ -473,8 +484,9 @@ __global__ void __launch_bounds__(kThreads) k_rollout(const __grid_constant__ Ro
   uint32_t acc[SUS_N_STATS];
 #pragma unroll
   for (int k = 0; k < SUS_N_STATS; ++k) acc[k] = 0;
+  const uint64_t tick0 = p.tick_dev ? __ldg(p.tick_dev) : p.tick0;
   for (int t = 0; t < p.n_steps; ++t) {
-    const uint64_t tick = p.tick0 + (uint64_t)t;
+    const uint64_t tick = tick0 + (uint64_t)t;
     if (have) {
       uint64_t acts = 0;
       WordStream wa;
@@ -797,7 +809,7 @@ __global__ void __launch_bounds__(kThreads) k_sample_actions(const __grid_consta
   if (e < p.N) {
     const uint32_t imp = (p.st.aux[e].x >> 8) & 0xff;
     WordStream wa;
-    wa.init(p.c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, p.tick, P_ACT);
+    wa.init(p.c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, launch_tick(p), P_ACT);
     for (int i = 0; i < A; ++i)  // base.py:326-330 (R6): dead agents are sampled too
       stage[warp][lane * A + i] = (int32_t)bounded(wa.word(i), role_actions_rt(p.c, (imp >> i) & 1u));
   }
@@ -1325,8 +1337,20 @@ struct SusEnv {
   double* ret;       // [A][N] + 2 trailing sums, allocated by sus_env_track_returns
   double gamma;
   uint64_t step_tick, reset_epoch, act_epoch;
+  uint64_t* dev_ticks;  // [3] = {step_tick, reset_epoch, act_epoch} in device memory once sus_env_device_ticks enabled them
   const uint32_t *inj_step, *inj_reset, *inj_act;
 };
+
+enum { TICK_STEP = 0, TICK_RESET = 1, TICK_ACT = 2 };
+
+namespace {
+// device-resident ticks: the counter a launch read is bumped by a one-thread kernel right behind it on the same stream
+int advance_tick(SusEnv* e, int which, uint64_t n, cudaStream_t st) {
+  if (!e->dev_ticks || n == 0) return SUS_OK;
+  k_advance_tick<<<1, 1, 0, st>>>(e->dev_ticks + which, n);
+  return after_launch("k_advance_tick");
+}
+}  // namespace
 
 extern "C" {
 
@@ -1399,7 +1423,7 @@ int sus_env_destroy(sus_env_t e) {
   DeviceGuard g(e->device);
   cudaDeviceSynchronize();
   cudaFree(e->st.pos); cudaFree(e->st.jobpos); cudaFree(e->st.aux); cudaFree(e->st.met);
-  cudaFree(e->stats); cudaFree(e->err); cudaFree(e->ret);
+  cudaFree(e->stats); cudaFree(e->err); cudaFree(e->ret); cudaFree(e->dev_ticks);
   delete e;
   return SUS_OK;
 }
@@ -1409,14 +1433,26 @@ int sus_env_reset(sus_env_t e, const uint8_t* mask, void* stream) {
   DeviceGuard g(e->device);
   ResetParams p;
   p.c = e->dc; p.st = e->st; p.mask = mask; p.inj_reset = e->inj_reset; p.tick = e->reset_epoch++; p.N = e->N;
+  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_RESET : nullptr;
   e->inj_reset = nullptr;
-  if (e->N == 0) return SUS_OK;
-  k_reset<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
-  return after_launch("k_reset");
+  if (e->N > 0) {
+    k_reset<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
+    if (int rc = after_launch("k_reset")) return rc;
+  }
+  return advance_tick(e, TICK_RESET, 1, (cudaStream_t)stream);
 }
+
+static int step_launch(sus_env_t e, const SusStepIO* io, void* stream);
 
 int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   if (!e || !io) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  const uint64_t before = e->step_tick;
+  if (int rc = step_launch(e, io, stream)) return rc;
+  DeviceGuard g(e->device);
+  return advance_tick(e, TICK_STEP, e->step_tick - before, (cudaStream_t)stream);  // (no tick was taken on an argument error)
+}
+
+static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
   if (io->actions && io->actions_dtype != SUS_U8 && io->actions_dtype != SUS_I32 && io->actions_dtype != SUS_I64)
     return fail(SUS_ERR_INVALID_ARGUMENT, "actions_dtype must be SUS_U8, SUS_I32 or SUS_I64");
   if (io->rewards && io->rewards_dtype != SUS_F32 && io->rewards_dtype != SUS_F64)
@@ -1435,6 +1471,7 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   p.metrics = reinterpret_cast<long long*>(io->metrics); p.imposters = io->imposters; p.spatial = io->spatial; p.non_spatial = io->non_spatial;
   p.inj_step = e->inj_step; p.inj_reset = e->inj_reset; p.inj_act = e->inj_act;
   p.stats = e->stats; p.err = e->err; p.tick = e->step_tick++; p.N = e->N;
+  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_STEP : nullptr;
   p.ret = e->ret; p.ret_sums = e->ret ? e->ret + (size_t)e->N * p.c.A : nullptr; p.gamma = e->gamma;
   e->inj_step = e->inj_reset = e->inj_act = nullptr;
   if (e->N == 0) return SUS_OK;
@@ -1546,9 +1583,10 @@ int sus_env_rollout(sus_env_t e, int32_t n_steps, double* reward_sums, void* str
   DeviceGuard g(e->device);
   RolloutParams p;
   p.c = e->dc; p.st = e->st; p.stats = e->stats; p.reward_sums = reward_sums; p.tick0 = e->step_tick; p.N = e->N;
+  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_STEP : nullptr;
   p.n_steps = n_steps;
   e->step_tick += (uint64_t)n_steps;
-  if (e->N == 0 || n_steps == 0) return SUS_OK;
+  if (e->N == 0 || n_steps == 0) return advance_tick(e, TICK_STEP, (uint64_t)n_steps, (cudaStream_t)stream);
   const unsigned gr = grid_for(e->N);
   cudaStream_t st = (cudaStream_t)stream;
   const int dA = p.c.A, dJ = p.c.J;
@@ -1566,7 +1604,8 @@ int sus_env_rollout(sus_env_t e, int32_t n_steps, double* reward_sums, void* str
       break;
   }
 #undef SUS_LAUNCH_ROLLOUT
-  return after_launch("k_rollout");
+  if (int rc = after_launch("k_rollout")) return rc;
+  return advance_tick(e, TICK_STEP, (uint64_t)n_steps, st);
 }
 
 int sus_env_check_actions(sus_env_t e, void* stream) {
@@ -1584,15 +1623,16 @@ int sus_env_check_actions(sus_env_t e, void* stream) {
 
 int sus_env_sample_actions(sus_env_t e, int32_t* out, void* stream) {
   if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
-  if (e->N == 0) { e->act_epoch++; e->inj_act = nullptr; return SUS_OK; }
-  if (!out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   DeviceGuard g(e->device);
+  if (e->N == 0) { e->act_epoch++; e->inj_act = nullptr; return advance_tick(e, TICK_ACT, 1, (cudaStream_t)stream); }
+  if (!out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   ActParams p;
   p.c = e->dc; p.st = e->st; p.out = out; p.inj_act = e->inj_act; p.tick = e->act_epoch++; p.N = e->N;
+  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_ACT : nullptr;
   e->inj_act = nullptr;
-  if (e->N == 0) return SUS_OK;
   k_sample_actions<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
-  return after_launch("k_sample_actions");
+  if (int rc = after_launch("k_sample_actions")) return rc;
+  return advance_tick(e, TICK_ACT, 1, (cudaStream_t)stream);
 }
 
 int sus_env_export_flat(sus_env_t e, int32_t dtype, void* out, void* stream) {
@@ -1792,8 +1832,37 @@ int sus_env_return_sums(sus_env_t e, double* out, void* stream) {
   return SUS_OK;
 }
 
+int sus_env_device_ticks(sus_env_t e, int32_t enable, void* stream) {
+  if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  DeviceGuard g(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (enable && !e->dev_ticks) {
+    uint64_t* d = nullptr;
+    SUS_CUDA(cudaMalloc(&d, 3 * sizeof(uint64_t)));
+    const uint64_t h[3] = {e->step_tick, e->reset_epoch, e->act_epoch};
+    SUS_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+    SUS_CUDA(cudaStreamSynchronize(st));
+    e->dev_ticks = d;
+  } else if (!enable && e->dev_ticks) {
+    uint64_t h[3];
+    SUS_CUDA(cudaDeviceSynchronize());
+    SUS_CUDA(cudaMemcpy(h, e->dev_ticks, sizeof(h), cudaMemcpyDeviceToHost));
+    e->step_tick = h[0]; e->reset_epoch = h[1]; e->act_epoch = h[2];
+    SUS_CUDA(cudaFree(e->dev_ticks));
+    e->dev_ticks = nullptr;
+  }
+  return SUS_OK;
+}
+
 int sus_env_get_ticks(sus_env_t e, uint64_t* step_tick, uint64_t* reset_epoch, uint64_t* act_epoch) {
   if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
+  if (e->dev_ticks) {  // the device holds the truth (graph replays advance it without the host): synchronises
+    DeviceGuard g(e->device);
+    uint64_t h[3];
+    SUS_CUDA(cudaDeviceSynchronize());
+    SUS_CUDA(cudaMemcpy(h, e->dev_ticks, sizeof(h), cudaMemcpyDeviceToHost));
+    e->step_tick = h[0]; e->reset_epoch = h[1]; e->act_epoch = h[2];
+  }
   if (step_tick) *step_tick = e->step_tick;
   if (reset_epoch) *reset_epoch = e->reset_epoch;
   if (act_epoch) *act_epoch = e->act_epoch;
@@ -1803,6 +1872,12 @@ int sus_env_get_ticks(sus_env_t e, uint64_t* step_tick, uint64_t* reset_epoch, u
 int sus_env_set_ticks(sus_env_t e, uint64_t step_tick, uint64_t reset_epoch, uint64_t act_epoch) {
   if (!e) return fail(SUS_ERR_INVALID_ARGUMENT, "env is NULL");
   e->step_tick = step_tick; e->reset_epoch = reset_epoch; e->act_epoch = act_epoch;
+  if (e->dev_ticks) {
+    DeviceGuard g(e->device);
+    const uint64_t h[3] = {step_tick, reset_epoch, act_epoch};
+    SUS_CUDA(cudaDeviceSynchronize());
+    SUS_CUDA(cudaMemcpy(e->dev_ticks, h, sizeof(h), cudaMemcpyHostToDevice));
+  }
   return SUS_OK;
 }
 

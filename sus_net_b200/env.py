@@ -519,6 +519,13 @@ class BatchedFourRoomEnv:
         L.check(self.lib.sus_env_rollout(self._h, int(n_steps), _ptr(out), self._stream()))
         return out
 
+    def device_ticks(self, enable=True):
+        """Keep the Philox launch ticks in device memory so that `reset` / `sample_actions` / `step` / `rollout` launches
+        can be captured in a CUDA graph (`torch.cuda.graph`) and replayed: every replay advances the ticks on the device
+        and gives the same results as the individual calls would.  With host ticks (the default) a replayed launch would
+        repeat its draws.  Costs one extra one-thread launch per call."""
+        L.check(self.lib.sus_env_device_ticks(self._h, int(bool(enable)), self._stream()))
+
     def check_actions(self):
         """Raise IndexError if any step since the last check saw an index outside an agent's role list."""
         L.check(self.lib.sus_env_check_actions(self._h, self._stream()))

@@ -426,6 +426,56 @@ def test_unaligned_output_pointers_through_the_c_abi(cuda_lib):
                 assert (cpu(ns_raw[:off]) == -7).all() and (cpu(ns_raw[off + ns_n:]) == -7).all()
 
 
+@pytest.mark.parametrize("name", ["cfg4_base_1v4", "cfg3_tagging_1v2", "cfg2_itg_1v1_wall"])
+def test_cuda_graph_replay_matches_oracle(cuda_lib, name, store_path):
+    """Device-resident ticks: a captured graph of [sample_actions, step (+ fused encode), 3-step rollout] replayed K times
+    walks the same trajectory as the oracle doing the same calls one by one; afterwards the env keeps stepping in
+    lock-step with host calls, and the checkpointed ticks are the advanced ones."""
+    import sus_net_b200 as S
+
+    cfg = CASES[name]
+    N, K = 777, 25
+    env = make_cuda_env(cfg, N, seed=21)
+    orc = oracle.OracleEnv(cfg, N, seed=21)
+    feat = S.GlobalFeaturizer(env) if name in GLOBAL_CASES else None
+    env.reset(); orc.reset()
+    env.device_ticks(True)
+    env.step(env.sample_actions(), featurizer=feat)  # eager warm-up call (loads the kernels' attributes outside the capture)
+    orc.step(orc.sample_actions())
+    side = torch.cuda.Stream(env.device)
+    side.wait_stream(torch.cuda.current_stream(env.device))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        env.rollout(3)  # warm-up of the rollout kernel as well
+        orc_r = [orc.step(None) for _ in range(3)]
+        with torch.cuda.graph(graph, stream=side):
+            acts = env.sample_actions()
+            nf, r, d, tr, _ = env.step(acts, featurizer=feat)
+            env.rollout(3)
+    torch.cuda.current_stream(env.device).wait_stream(side)
+    del orc_r
+    for k in range(K):
+        graph.replay()
+        o = orc.step(orc.sample_actions())
+        want_cur = orc.flat_states()
+        for _ in range(3):
+            orc.step(None)
+        if k % 6 == 0 or k == K - 1:
+            assert np.array_equal(cpu(nf).astype(np.int64), o["next_flat"]), f"{name}: replay {k}"
+            assert np.array_equal(cpu(r), o["rewards"].astype(np.float32)) and np.array_equal(cpu(d), o["done"] != 0)
+            if feat is not None:
+                sp, ns = oracle.encode_global(cfg, want_cur)
+                views = feat.generate_featurized_states()
+                assert np.array_equal(cpu(views[0][0])[:, 0], sp) and np.array_equal(cpu(views[2][1])[:, 0], ns[2])
+            assert np.array_equal(cpu(env.flat_states(torch.int64)), orc.flat_states()), f"{name}: replay {k}"
+    assert np.array_equal(cpu(env.episode_stats()), orc.stats())
+    sd = env.state_dict()
+    assert sd["ticks"][0] == 1 + 3 + 4 * K and sd["ticks"][2] == 1 + K  # step ticks / act epochs advanced on the device
+    env.device_ticks(False)  # back to host ticks: they continue from the device's values
+    nf2, *_ = env.step(None)
+    assert np.array_equal(cpu(nf2).astype(np.int64), orc.step(None)["next_flat"])
+
+
 def test_flat_rows_unaligned_and_ragged_through_the_c_abi(cuda_lib):
     """Flat rows with an odd float count (F = 39) on ragged env counts, written to 4-byte-aligned tensors by the standalone
     encode AND by the fused step (rewards / replay row / features all unaligned): the staged paths must fall back to scalar
