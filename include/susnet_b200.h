@@ -281,6 +281,16 @@ typedef struct SusReplayPush {
 /* ReplayBuffer.add (replay_memory.py:50-72) for a whole batched step; the caller advances idx/size. */
 int sus_replay_push(const SusReplayPush *args /*host*/, int device, void *stream);
 
+/* L2-compressible device memory for the feature tensors (no reference analogue; the reference's tensors live in host
+ * memory).  The planes and flat rows are almost all zeros; in an allocation made with cuMemCreate +
+ * CU_MEM_ALLOCATION_COMP_GENERIC Blackwell's L2 keeps such lines compressed on their way to and from HBM (measured on
+ * B200: the fused kernel's tile-store stream 6.4 -> 7.5 TB/s, reading the tiles back 6.9 -> 9.3 TB/s).  Any pointer this
+ * library takes may point into such a block.  `bytes` is rounded up to the allocation granularity (2 MiB); `allocated`
+ * (optional) receives the rounded size.  SUS_ERR_UNSUPPORTED if the device or driver has no generic compression.
+ * sus_free_compressible synchronises the device. */
+int sus_alloc_compressible(int device, uint64_t bytes, void **ptr /*host*/, uint64_t *allocated /*host, may be NULL*/);
+int sus_free_compressible(void *ptr);
+
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t sus_launch_count(void);
 

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "sus_env_export_metrics", "sus_env_encode", "sus_encode_from_flat", "sus_env_stats", "sus_env_clear_stats",
     "sus_env_get_ticks", "sus_env_set_ticks", "sus_env_state_arrays", "sus_env_debug_inject_words",
     "sus_launch_count", "sus_replay_push", "sus_env_rollout", "sus_env_track_returns", "sus_env_return_sums",
-    "sus_env_device_ticks",
+    "sus_env_device_ticks", "sus_alloc_compressible", "sus_free_compressible",
 )
 
 
@@ -111,6 +111,8 @@ def lib():
         "sus_env_get_ticks": ([vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)], C.c_int),
         "sus_env_set_ticks": ([vp, u64, u64, u64], C.c_int),
         "sus_env_device_ticks": ([vp, i32, vp], C.c_int),
+        "sus_alloc_compressible": ([C.c_int, u64, C.POINTER(vp), C.POINTER(u64)], C.c_int),
+        "sus_free_compressible": ([vp], C.c_int),
         "sus_env_state_arrays": ([vp, C.POINTER(vp), C.POINTER(i32)], C.c_int),
         "sus_env_debug_inject_words": ([vp, vp, vp, vp], C.c_int),
         "sus_launch_count": ([], i64),

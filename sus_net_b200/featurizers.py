@@ -16,6 +16,7 @@ import torch
 
 from . import _lib as L
 from .env import StateFields, _ptr, _TORCH_TO_SUS
+from .memory import empty_f32
 
 
 # ---------------------------------------------------------------------------------------------- components
@@ -171,9 +172,9 @@ class SequenceStateFeaturizer:
         if n_items not in self._buffers:
             if len(self._buffers) >= 4:
                 self._buffers.pop(next(iter(self._buffers)))
-            sp = (torch.empty((sh.spatial_views, n_items, sh.spatial_floats), dtype=torch.float32, device=dev)
-                  if sh.spatial_views else None)
-            ns = torch.empty((sh.non_spatial_views, n_items, sh.non_spatial_floats), dtype=torch.float32, device=dev)
+            # the output tensors are almost all zeros: L2-compressible memory where the device has it (memory.py)
+            sp = empty_f32((sh.spatial_views, n_items, sh.spatial_floats), dev) if sh.spatial_views else None
+            ns = empty_f32((sh.non_spatial_views, n_items, sh.non_spatial_floats), dev)
             self._buffers[n_items] = (sp, ns)
         self._sp_buf, self._ns_buf = self._buffers[n_items]
 

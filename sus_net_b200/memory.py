@@ -1,0 +1,58 @@
+"""Device buffers for the feature tensors in L2-compressible memory (`sus_alloc_compressible`, csrc/susnet_alloc.cu).
+
+The planes / flat rows are almost all zeros; in a compressible allocation the B200's L2 keeps such lines compressed on
+their way to and from HBM, which is worth +18 % on the fused kernel's tile-store stream and +35 % on reading the
+tensors back (tools/micro/compressible_bench.cu).  torch's own allocator cannot make such allocations, so the featurizers
+get their buffers here; small buffers, devices without generic compression and `SUSNET_COMPRESSIBLE=0` use `torch.empty`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+MIN_BYTES = 4 << 20  # below this a 2 MiB-granular private allocation is not worth it
+_unsupported = set()  # device indices that refused a compressible allocation
+
+
+class _Block:
+    """Owner of one compressible allocation; tensors made from it keep it alive (torch holds a reference to the object
+    that exports __cuda_array_interface__ until the storage dies) and the memory is unmapped when the last one goes."""
+
+    def __init__(self, lib, ptr, shape):
+        self._lib, self._ptr = lib, ptr
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+    def __del__(self):
+        try:
+            self._lib.sus_free_compressible(C.c_void_p(self._ptr))
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+def compressible_enabled():
+    return os.environ.get("SUSNET_COMPRESSIBLE", "1") != "0"
+
+
+def empty_f32(shape, device):
+    """Uninitialised float32 tensor of `shape` on `device`, in L2-compressible memory where that applies."""
+    device = torch.device(device)
+    nbytes = 4 * int(np.prod(shape))
+    if compressible_enabled() and nbytes >= MIN_BYTES and device.index not in _unsupported:
+        lib = L.lib()
+        ptr = C.c_void_p()
+        rc = lib.sus_alloc_compressible(device.index, nbytes, C.byref(ptr), None)
+        if rc == L.SUS_OK:
+            t = torch.as_tensor(_Block(lib, ptr.value, shape), device=device)
+            t._sus_compressible = True
+            return t
+        if rc != L.SUS_ERR_UNSUPPORTED:
+            L.check(rc)
+        _unsupported.add(device.index)
+    return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+
+
+def is_compressible(t):
+    return bool(getattr(t, "_sus_compressible", False))
