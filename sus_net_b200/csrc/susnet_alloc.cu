@@ -121,6 +121,17 @@ int sus_alloc_compressible(int device, uint64_t bytes, void** ptr, uint64_t* all
   return SUS_OK;
 }
 
+// (library-internal) does `p` point into a live compressible block?  The launch heuristics differ: stores into such a
+// block drain faster, which moves the balance between the compute warps and the emitter warp of k_step_ws.
+int sus_internal_is_compressible(const void* p) {
+  if (!p) return 0;
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_blocks.upper_bound((uintptr_t)p);
+  if (it == g_blocks.begin()) return 0;
+  --it;
+  return (uintptr_t)p < it->first + it->second.size ? 1 : 0;
+}
+
 int sus_free_compressible(void* ptr) {
   if (!ptr) return SUS_OK;
   Block b;

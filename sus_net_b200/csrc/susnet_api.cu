@@ -1236,11 +1236,19 @@ bool make_flat_stage(const DevConfig& c, const DevEncode& enc, int rew_elem, boo
 }
 
 // Warp-specialised layout (susnet_ws.cuh); returns false if it does not apply or does not fit.
-bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, WsLayout& L) {
+// `fast_sink`: the plane tensor lives in L2-compressible memory (sus_alloc_compressible), where the tile stores drain
+// ~18 % faster.  Measured at 1 Mi envs (tools/ab_flat.py under SUSNET_WS_TILE / SUSNET_WS_WARPS): Global into a fast sink
+// is compute-bound and best with 8-env tiles + 7 compute warps (8 warps = 2 per scheduler: 0.381 ms against 0.403 with 6
+// and 0.412 with 8); everything else is emitter-bound and best with 6 (Global into cudaMalloc memory 0.465 against
+// 0.504 with 7, Perspective 0.399 against 0.414).
+// The encode-only kernels pass step = false and take as many (cheap) row-parsing warps as fit, as before.
+bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, bool step,
+                    bool fast_sink, WsLayout& L) {
   if (enc.sp_floats <= 0 || (enc.kind != SUS_ENCODE_GLOBAL && enc.kind != SUS_ENCODE_PERSPECTIVE)) return false;
   WsLayout t = {};
+  const bool compute_bound = step && fast_sink && enc.kind == SUS_ENCODE_GLOBAL;
   const char* env_te = std::getenv("SUSNET_WS_TILE");
-  t.tile_envs = (env_te && std::atoi(env_te) == 8) ? 8 : 16;
+  t.tile_envs = env_te ? (std::atoi(env_te) == 8 ? 8 : 16) : (compute_bound ? 8 : 16);
   t.tile_bytes = align128((int64_t)t.tile_envs * enc.sp_floats * 4);
   if (t.tile_envs == 16 && max_dyn_smem - 2048 - 2 * t.tile_bytes - 512 < 4 * (32 * 32 + align128((int64_t)c.A * 32 * enc.ns_floats * 4) + align128((int64_t)32 * c.A * rew_elem))) {
     t.tile_envs = 8;  // big configs: fall back to 8-env tiles so that at least two compute warps fit
@@ -1256,7 +1264,8 @@ bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool
   int cw = budget / (2 * t.slot_bytes);
   if (cw > kWsMaxWarps - 1) cw = kWsMaxWarps - 1;
   const char* env_w = std::getenv("SUSNET_WS_WARPS");
-  if (env_w && std::atoi(env_w) > 0 && std::atoi(env_w) < cw) cw = std::atoi(env_w);
+  const int want_cw = env_w && std::atoi(env_w) > 0 ? std::atoi(env_w) : (!step ? cw : (compute_bound ? 7 : 6));
+  if (want_cw < cw) cw = want_cw;
   if (cw < 2) return false;
   t.compute_warps = cw;
   t.slots_off = 2 * t.tile_bytes;
@@ -1351,6 +1360,8 @@ int advance_tick(SusEnv* e, int which, uint64_t n, cudaStream_t st) {
   return after_launch("k_advance_tick");
 }
 }  // namespace
+
+extern "C" int sus_internal_is_compressible(const void* p);  // susnet_alloc.cu
 
 extern "C" {
 
@@ -1483,7 +1494,7 @@ static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
   // higher occupancy wins there (measured 14.6e9 vs 7.3e9 env-steps/s); the TMA path pays off once features are written
   WsLayout W;
   if (want_ws() && enc && make_ws_layout(p.c, p.enc, io->rewards_dtype == SUS_F64 ? 8 : 4, io->next_flat != nullptr,
-                                         di.max_dyn_smem, W)) {
+                                         di.max_dyn_smem, true, sus_internal_is_compressible(io->spatial) != 0, W)) {
     const int64_t groups = (e->N + 31) / 32;
     const int64_t ctas = (groups + W.compute_warps - 1) / W.compute_warps;
     const unsigned gr = (unsigned)(ctas < di.sms ? ctas : di.sms);
@@ -1702,7 +1713,7 @@ int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float
   DeviceInfo di;
   if (int rc = device_info(e->device, di)) return rc;
   WsLayout W;
-  if (want_ws() && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, W)) {
+  if (want_ws() && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, false, false, W)) {
     if (int rc = allow_big_smem(k_encode_ws<float, false>, W.total_bytes)) return rc;
     k_encode_ws<float, false><<<ws_grid(e->N, W, di.sms), (W.compute_warps + 1) * 32, W.total_bytes, (cudaStream_t)stream>>>(p, W);
     return after_launch("k_encode_ws");
@@ -1748,7 +1759,7 @@ int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const 
   DeviceInfo di;
   if (int rc = device_info(device, di)) return rc;
   WsLayout W;
-  if (want_ws() && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, W)) {
+  if (want_ws() && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, false, false, W)) {
     const unsigned gr = ws_grid(n_items, W, di.sms), threads = (unsigned)(W.compute_warps + 1) * 32;
     if (dtype == SUS_F32) {
       if (int rc = allow_big_smem(k_encode_ws<float, true>, W.total_bytes)) return rc;
