@@ -476,6 +476,53 @@ def test_cuda_graph_replay_matches_oracle(cuda_lib, name, store_path):
     assert np.array_equal(cpu(nf2).astype(np.int64), orc.step(None)["next_flat"])
 
 
+def test_compressible_feature_memory(cuda_lib, monkeypatch):
+    """sus_alloc_compressible: the featurizers' big output buffers live in L2-compressible memory (where the device has
+    it), results are identical to the ones written into torch-allocated memory, small buffers stay with torch, blocks are
+    freed with their last tensor and a foreign / repeated free is refused."""
+    import ctypes as C
+    import gc
+
+    import sus_net_b200 as S
+    from sus_net_b200 import _lib as L
+    from sus_net_b200 import memory as M
+
+    lib = L.lib()
+    ptr, got = C.c_void_p(), C.c_uint64()
+    rc = lib.sus_alloc_compressible(0, 5 << 20, C.byref(ptr), C.byref(got))
+    if rc == L.SUS_ERR_UNSUPPORTED:
+        pytest.skip("device without generic compression")
+    L.check(rc)
+    assert ptr.value and got.value >= 5 << 20 and got.value % (2 << 20) == 0
+    L.check(lib.sus_free_compressible(ptr))
+    with pytest.raises(AssertionError):
+        L.check(lib.sus_free_compressible(ptr))  # not a live block any more
+    with pytest.raises(AssertionError):
+        L.check(lib.sus_alloc_compressible(0, 0, C.byref(ptr), None))
+
+    cfg = CASES["cfg4_base_1v4"]
+    N = 8192  # planes: 8192 x 567 x 4 B = 18.6 MB (compressible); non-spatial views: 2.5 MB (torch)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SUSNET_COMPRESSIBLE", flag)
+        env = make_cuda_env(cfg, N, seed=4)
+        feat = S.GlobalFeaturizer(env)
+        env.reset()
+        for _ in range(5):
+            env.step(None, featurizer=feat)
+        assert M.is_compressible(feat._sp_buf) == (flag == "1") and not M.is_compressible(feat._ns_buf)
+        views = feat.generate_featurized_states()
+        outs.append((cpu(views[0][0]).copy(), cpu(views[3][1]).copy(), cpu(env.flat_states(torch.int64))))
+        t = feat._sp_buf
+        del feat, views, env
+        gc.collect()
+        assert float(t.sum()) > 0  # the tensor alone keeps its block mapped
+        del t
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))
+    small = M.empty_f32((16, 16), torch.device("cuda", 0))
+    assert not M.is_compressible(small)
+
+
 def test_flat_rows_unaligned_and_ragged_through_the_c_abi(cuda_lib):
     """Flat rows with an odd float count (F = 39) on ragged env counts, written to 4-byte-aligned tensors by the standalone
     encode AND by the fused step (rewards / replay row / features all unaligned): the staged paths must fall back to scalar
