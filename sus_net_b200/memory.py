@@ -15,6 +15,7 @@ from . import _lib as L
 
 MIN_BYTES = 4 << 20  # below this a 2 MiB-granular private allocation is not worth it
 _unsupported = set()  # device indices that refused a compressible allocation
+_deferred = []  # (lib, ptr) of blocks whose last tensor died during a CUDA graph capture; freed at the next allocation
 
 
 class _Block:
@@ -27,7 +28,10 @@ class _Block:
 
     def __del__(self):
         try:
-            self._lib.sus_free_compressible(C.c_void_p(self._ptr))
+            if torch.cuda.is_current_stream_capturing():
+                _deferred.append((self._lib, self._ptr))  # freeing synchronises the device: not inside a graph capture
+            else:
+                self._lib.sus_free_compressible(C.c_void_p(self._ptr))
         except Exception:  # noqa: BLE001 - interpreter shutdown
             pass
 
@@ -42,6 +46,9 @@ def empty_f32(shape, device):
     nbytes = 4 * int(np.prod(shape))
     if compressible_enabled() and nbytes >= MIN_BYTES and device.index not in _unsupported:
         lib = L.lib()
+        while _deferred and not torch.cuda.is_current_stream_capturing():
+            dlib, dptr = _deferred.pop()
+            dlib.sus_free_compressible(C.c_void_p(dptr))
         ptr = C.c_void_p()
         rc = lib.sus_alloc_compressible(device.index, nbytes, C.byref(ptr), None)
         if rc == L.SUS_OK:
