@@ -16,7 +16,10 @@
 //                              featurizers on live env state / on (B*T, S) flattened rows (= featurizer.fit)
 //   K3    k_sample_actions     role-aware uniform random actions
 //         k_rollout<V>         n random-policy steps per launch with the env state in registers
-//   plus small export / import kernels for the reference's flatten order (and k_replay_push in susnet_replay.cu).
+//         k_advance_tick       device-resident launch ticks (sus_env_device_ticks): makes the launches above replayable
+//                              inside CUDA graphs
+//   plus small export / import kernels for the reference's flatten order, k_replay_push (susnet_replay.cu) and the
+//   L2-compressible allocator the feature tensors live in (susnet_alloc.cu).
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
