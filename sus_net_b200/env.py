@@ -598,6 +598,9 @@ class BatchedFourRoomEnvWithTagging(BatchedFourRoomEnv):
 
     def __init__(self, *args, tag_reset_interval=50, vote_reward=3, **kwargs):
         super().__init__(*args, tag_reset_interval=tag_reset_interval, vote_reward=vote_reward, **kwargs)
+        # AmongUsVisualizer decides whether to draw the voting panel with `env.__dict__.get("tag_counts")`
+        # (visualize.py:153); the value itself comes from the property below (a data descriptor wins the lookup)
+        self.__dict__["tag_counts"] = "property"
 
     def _init_action_lists(self):
         super()._init_action_lists()

@@ -476,6 +476,36 @@ def test_cuda_graph_replay_matches_oracle(cuda_lib, name, store_path):
     assert np.array_equal(cpu(nf2).astype(np.int64), orc.step(None)["next_flat"])
 
 
+def test_viewer_surface_of_reference_mode(cuda_lib):
+    """The statements AmongUsVisualizer / run_game execute on the env (visualize.py:40-43,92,142,153-160,214-261,555-560),
+    without pygame: a reference-mode env exposes the same attributes with the shapes the viewer indexes."""
+    import sus_net_b200 as S
+    from sus_net_b200.metrics import SusMetrics
+
+    env = S.BatchedFourRoomEnvWithTagging(1, 3, 2, seed=3)
+    env.reset()
+    for _ in range(3):
+        env.step(env.sample_actions())
+    assert env.n_rows == 9 and env.n_cols == 9 and env.grid.shape == (9, 9)
+    assert env.__dict__.get("tag_counts") is not None  # the voting panel is drawn
+    vote_counts = env.tag_counts.flatten()
+    vote_counts[env.alive_agents == 0] = -1
+    voted = env.used_tag_actions.flatten() + 0
+    voted[env.alive_agents == 0] = -1
+    assert len(vote_counts) == 4 and len(voted) == 4
+    assert 0 < env.tag_reset_interval - env.tag_reset_timer <= env.tag_reset_interval
+    for i, (pos, alive) in enumerate(zip(env.agent_positions, env.alive_agents)):
+        x, y = pos
+        assert 0 <= x < 9 and 0 <= y < 9 and env.grid[x, y] and alive in (0, 1) and env.imposter_mask[i] in (True, False)
+    assert len(env.job_positions) == env.n_jobs == len(env.completed_jobs)
+    assert env.metrics.metrics[SusMetrics.IMPOSTER_WON] in (0, 1)
+    assert env.compute_action(0, 1) == str(S.Action.UP) and env.compute_action(1, 8) == "Vote Player 0"
+    assert any(i in env.imposter_idxs for i in range(env.n_agents))
+    assert env.flatten_state(env.reset()[0]).shape == (env.flattened_state_size,)
+    base = S.BatchedFourRoomEnv(1, 2, 1)
+    assert base.__dict__.get("tag_counts") is None  # no voting panel for the plain env
+
+
 def test_compressible_feature_memory(cuda_lib, monkeypatch):
     """sus_alloc_compressible: the featurizers' big output buffers live in L2-compressible memory (where the device has
     it), results are identical to the ones written into torch-allocated memory, small buffers stay with torch, blocks are
