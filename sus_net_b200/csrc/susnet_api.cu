@@ -1244,7 +1244,7 @@ bool make_flat_stage(const DevConfig& c, const DevEncode& enc, int rew_elem, boo
 // is compute-bound and best with 8-env tiles + 7 compute warps (8 warps = 2 per scheduler: 0.381 ms against 0.403 with 6
 // and 0.412 with 8); everything else is emitter-bound and best with 6 (Global into cudaMalloc memory 0.465 against
 // 0.504 with 7, Perspective 0.399 against 0.414).
-// The encode-only kernels pass step = false and take as many (cheap) row-parsing warps as fit, as before.
+// The encode-only kernels pass step = false (their row-parsing warps are cheap).
 bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, bool step,
                     bool fast_sink, WsLayout& L) {
   if (enc.sp_floats <= 0 || (enc.kind != SUS_ENCODE_GLOBAL && enc.kind != SUS_ENCODE_PERSPECTIVE)) return false;
@@ -1267,7 +1267,10 @@ bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool
   int cw = budget / (2 * t.slot_bytes);
   if (cw > kWsMaxWarps - 1) cw = kWsMaxWarps - 1;
   const char* env_w = std::getenv("SUSNET_WS_WARPS");
-  const int want_cw = env_w && std::atoi(env_w) > 0 ? std::atoi(env_w) : (!step ? cw : (compute_bound ? 7 : 6));
+  // encode-only launches: any count >= 5 is the same for Global (0.393-0.398 ms at 1 Mi rows); Perspective is best
+  // with 5 (0.419 ms at 256 Ki rows against 0.427 with 7-8 and 0.459 with 11)
+  const int want_cw = env_w && std::atoi(env_w) > 0 ? std::atoi(env_w)
+                      : (!step ? (enc.kind == SUS_ENCODE_PERSPECTIVE ? 5 : cw) : (compute_bound ? 7 : 6));
   if (want_cw < cw) cw = want_cw;
   if (cw < 2) return false;
   t.compute_warps = cw;
