@@ -367,6 +367,48 @@ def test_random_constructor_arguments_match_oracle(cuda_lib, k):
             assert all(np.array_equal(cpu(v[0])[:, 0], sp) and np.array_equal(cpu(v[1])[:, 0], ns[i]) for i, v in enumerate(views))
 
 
+@pytest.mark.parametrize("k", range(10))
+def test_random_flat_component_sets_match_oracle(cuda_lib, k):
+    """Random env configurations (any variant, up to 8 agents / 8 jobs) x random orderings of flat components, with and
+    without the float-valued scent component (i.e. byte-staged and float-row kernels): fused step + encode, the
+    standalone encode of the live state and fit() from float32 / float64 / int64 rows all equal the oracle's rows."""
+    from tests.cases import random_case
+
+    rng = np.random.default_rng(424200 + k)
+    cfg = random_case(rng)
+    names = ["onehot_pos", "coords", "alive_crew", "dist_to_imposter", "walls", "rooms", "state_alive"]
+    if cfg["n_imposters"] == 1:  # the per-crew components index crew by agent_idx - 1 (component.py:440,467)
+        names += ["closest_crew", "l1_crew"]
+    if cfg["n_jobs"] > 0:
+        names.append("state_job_status")
+    if cfg["variant"] == "tagging":
+        names += ["state_used_tags", "state_tag_counts"]
+    if k % 3 == 0:
+        names.append("scent")
+    comps = [names[i] for i in rng.permutation(len(names))[:int(rng.integers(1, len(names) + 1))]]
+    if k % 4 == 1:
+        comps.append("onehot_pos")  # a second one-hot segment in the same row
+    N, T = 1003, 40
+    env = make_cuda_env(cfg, N, seed=k, env_id_base=11 * k)
+    orc = oracle.OracleEnv(cfg, N, seed=k, env_id_base=11 * k)
+    env.reset(); orc.reset()
+    feat = flat_featurizer(env, comps)
+    for t in range(T):
+        env.step(None, featurizer=feat)
+        orc.step(None)
+        if t % 13 == 0 or t == T - 1:
+            want = oracle.encode_flat(cfg, comps, orc.flat_states())
+            got = cpu(feat.generate_featurized_states()[0][1])[:, 0]
+            assert np.array_equal(got.view(np.int32), want.view(np.int32)), f"fused rows differ at step {t}: {cfg} {comps}"
+    cur = orc.flat_states()
+    want = oracle.encode_flat(cfg, comps, cur)
+    assert np.array_equal(cpu(feat.encode_env()[0][1])[:, 0].view(np.int32), want.view(np.int32))
+    for dtype in (torch.float32, torch.float64, torch.int64):
+        feat.fit(torch.as_tensor(cur).to(dtype).reshape(N, 1, -1))
+        assert np.array_equal(cpu(feat.generate_featurized_states()[0][1])[:, 0].view(np.int32), want.view(np.int32)), str(dtype)
+    assert np.array_equal(cpu(env.flat_states(torch.int64)), cur)
+
+
 @pytest.mark.parametrize("name", ["cfg2_itg_1v1_wall", "cfg3_tagging_1v2", "cfg4_base_1v4", "base_2v3_j3"])
 def test_rollout_kernel_equals_repeated_steps(cuda_lib, name):
     """rollout(T) == T x step(None): final states, per-episode counters, episode statistics, reward sums."""
