@@ -15,10 +15,18 @@ class HostStepper:
         self.s_h2d, self.s_run, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
         assert actions_dtype in (torch.uint8, torch.int32, torch.int64)
         self.d_actions = [torch.empty((N, A), dtype=actions_dtype, device=dev) for _ in range(slots)]
-        self.d_out = [(torch.empty((N, A), dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.bool, device=dev),
-                       torch.empty(N, dtype=torch.bool, device=dev)) for _ in range(slots)]
-        self.h_out = [(torch.empty((N, A), dtype=torch.float32).pin_memory(), torch.empty(N, dtype=torch.bool).pin_memory(),
-                       torch.empty(N, dtype=torch.bool).pin_memory()) for _ in range(slots)]
+        # per slot ONE packed block [rewards (N, A) f32 | dones (N,) | truncated (N,)] on the device and in pinned host
+        # memory: the results of a step leave the device in a single D2H copy
+        nb_r = N * A * 4
+
+        def views(block):
+            return (block[:nb_r].view(torch.float32).view(N, A), block[nb_r:nb_r + N].view(torch.bool),
+                    block[nb_r + N:nb_r + 2 * N].view(torch.bool))
+
+        self.d_block = [torch.empty(nb_r + 2 * N, dtype=torch.uint8, device=dev) for _ in range(slots)]
+        self.h_block = [torch.empty(nb_r + 2 * N, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.d_out = [views(b) for b in self.d_block]
+        self.h_out = [views(b) for b in self.h_block]
         self.ev_h2d = [torch.cuda.Event() for _ in range(slots)]
         self.ev_run = [torch.cuda.Event() for _ in range(slots)]
         self.ev_d2h = [torch.cuda.Event() for _ in range(slots)]
@@ -33,7 +41,7 @@ class HostStepper:
 
     @property
     def d2h_bytes_per_step(self):
-        return sum(t.numel() * t.element_size() for t in self.d_out[0])
+        return self.d_block[0].numel()
 
     def step(self, host_actions):
         """Enqueue one step on `host_actions` ((N, A) of `actions_dtype`, ideally pinned).  Returns the slot whose pinned host
@@ -53,8 +61,7 @@ class HostStepper:
             self.ev_run[slot].record(self.s_run)
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(self.ev_run[slot])
-            for h, d in zip(self.h_out[slot], self.d_out[slot]):
-                h.copy_(d, non_blocking=True)
+            self.h_block[slot].copy_(self.d_block[slot], non_blocking=True)
             self.ev_d2h[slot].record(self.s_d2h)
         self.k += 1
         return slot
