@@ -7,6 +7,7 @@ get their buffers here; small buffers, devices without generic compression and `
 """
 import ctypes as C
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -55,8 +56,9 @@ def empty_f32(shape, device):
             t = torch.as_tensor(_Block(lib, ptr.value, shape), device=device)
             t._sus_compressible = True
             return t
-        if rc != L.SUS_ERR_UNSUPPORTED:
-            L.check(rc)
+        if rc != L.SUS_ERR_UNSUPPORTED:  # e.g. the driver refuses virtual-memory allocations in this container: say so once
+            warnings.warn(f"sus_alloc_compressible failed ({lib.sus_last_error().decode()}); feature tensors of cuda:{device.index} "
+                          "stay in ordinary device memory", RuntimeWarning, stacklevel=2)
         _unsupported.add(device.index)
     return torch.empty(tuple(shape), dtype=torch.float32, device=device)
 
