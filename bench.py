@@ -17,7 +17,10 @@ Numbers on the JSON line
             host memory (D2H); the
             feature tensors stay on the device, where the Q-network consumes them
   roofline  achieved = 2650 algorithmic bytes per env-step x envs per launch / mean duration of the
-            fused step+encode kernel, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+            fused step+encode kernel, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.  The feature
+            tensors live in L2-compressible memory, so the DRAM bytes per launch (`traffic`, from the ncu capture in
+            profiles/) are about a third of the algorithmic bytes and `frac` can exceed 1; `store_stream` gives the
+            fraction of the bare SM -> L2 bulk-store stream, which is what binds the kernel then
   cpu_baseline   the oracle's C port of the reference loop (sample_actions + step + Global encode) timed on this
             box's host cores (kind "port": the reference is pure Python and cannot travel to the GPU box)
 Environments are independent: ranks own disjoint env-id ranges (weak scaling, no collective on the step path);
@@ -436,8 +439,10 @@ def run_b200_arm(args):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "global_envs": world * N,
                        "parallelism": f"env-sharded x{world}, no step-path collective",
-                       "l2": f"per-step working set {N * (ALGO_BYTES_STEP_ENCODE + 48) / 1e6:.0f} MB per GPU (> 126 MB L2) "
-                             "rewritten every step; no L2 flush needed"},
+                       "l2": f"per-step working set {N * (ALGO_BYTES_STEP_ENCODE + 48) / 1e6:.0f} MB per GPU rewritten every step "
+                             + (f"({roofline['traffic'] / 1e6:.0f} MB of DRAM traffic per step after L2 compression) "
+                                if roofline.get("traffic") and roofline["traffic"] < 0.9 * N * ALGO_BYTES_STEP_ENCODE else "")
+                             + "(> 126 MB L2); no L2 flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "extra": {"sample_actions_kernel_ms": sample_ms, "fused_random_policy_env_steps_per_s": fused_policy_value,
                       "step_only_env_steps_per_s": step_only_value,
