@@ -44,7 +44,11 @@ int main(int argc, char **argv) {
   CUDA(cudaMalloc((void **)&rewards, (size_t)N * A * sizeof(float)));
   CUDA(cudaMalloc((void **)&done, (size_t)N));
   CUDA(cudaMalloc((void **)&trunc, (size_t)N));
-  CUDA(cudaMalloc((void **)&spatial, (size_t)shape.spatial_views * N * shape.spatial_floats * sizeof(float)));
+  /* the planes are almost all zeros: put them in L2-compressible memory where the device has it */
+  const uint64_t sp_bytes = (uint64_t)shape.spatial_views * N * shape.spatial_floats * sizeof(float);
+  int compressible = sus_alloc_compressible(0, sp_bytes, (void **)&spatial, NULL) == SUS_OK;
+  if (!compressible) CUDA(cudaMalloc((void **)&spatial, sp_bytes));
+  printf("plane tensor in %s memory\n", compressible ? "L2-compressible" : "cudaMalloc");
   CUDA(cudaMalloc((void **)&non_spatial, (size_t)shape.non_spatial_views * N * shape.non_spatial_floats * sizeof(float)));
   CUDA(cudaMalloc((void **)&stats, SUS_N_STATS * sizeof(int64_t)));
 
@@ -80,6 +84,7 @@ int main(int argc, char **argv) {
   const int ok = h_stats[SUS_S_EPISODES] == h_stats[SUS_S_CREW_WON] + h_stats[SUS_S_IMPOSTER_WON] + h_stats[SUS_S_TRUNCATED] &&
                  ones / (double)N >= 5.0 && ones / (double)N <= A + 5.0;
   free(h_sp);
+  if (compressible) CHECK(sus_free_compressible(spatial));
   CHECK(sus_env_destroy(env));
   printf(ok ? "OK\n" : "MISMATCH\n");
   return ok ? 0 : 2;
