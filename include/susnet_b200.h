@@ -231,10 +231,10 @@ int sus_env_return_sums(sus_env_t env, double *out, void *stream);
 
 /* Device-resident launch ticks.  By default the tick of a launch (the Philox counter word that makes step t differ from
  * step t+1) is a host counter passed as a kernel parameter, so a captured CUDA graph would replay the SAME draws.  With
- * enable != 0 the three counters live in device memory: every launch reads its tick there and a one-thread kernel
- * behind it on the same stream advances it, which makes reset / sample_actions / step / rollout launches capturable in
- * a CUDA graph and replayable any number of times with the same results as individual calls (no reference analogue: the
- * reference has no launches to amortise).  sus_env_get_ticks / sus_env_set_ticks then synchronise the device.
+ * enable != 0 the three counters live in device memory: every launch reads its tick there and the last of its thread
+ * blocks to have read it advances it for the next launch (no extra launch), which makes reset / sample_actions / step /
+ * rollout launches capturable in a CUDA graph and replayable any number of times with the same results as individual
+ * calls (no reference analogue: the reference has no launches to amortise).  sus_env_get_ticks / sus_env_set_ticks then synchronise the device.
  * enable == 0 copies the counters back to the host and returns to kernel-parameter ticks.  Not during a capture. */
 int sus_env_device_ticks(sus_env_t env, int32_t enable, void *stream);
 

@@ -16,8 +16,8 @@
 //                              featurizers on live env state / on (B*T, S) flattened rows (= featurizer.fit)
 //   K3    k_sample_actions     role-aware uniform random actions
 //         k_rollout<V>         n random-policy steps per launch with the env state in registers
-//         k_advance_tick       device-resident launch ticks (sus_env_device_ticks): makes the launches above replayable
-//                              inside CUDA graphs
+//         device-resident launch ticks (sus_env_device_ticks, fetch_launch_tick in susnet_device.cuh) make the
+//         launches above replayable inside CUDA graphs
 //   plus small export / import kernels for the reference's flatten order, k_replay_push (susnet_replay.cu) and the
 //   L2-compressible allocator the feature tensors live in (susnet_alloc.cu).
 #include <atomic>
@@ -91,7 +91,8 @@ struct StepParams {
   double* ret_sums;  // [2] sums over finished episodes of mean imposter / mean crew return (train.py:421-424)
   double gamma;
   uint64_t tick;
-  const uint64_t* tick_dev;  // device-resident tick (sus_env_device_ticks) or nullptr: use `tick`
+  uint64_t* tick_dev;        // device-resident tick (sus_env_device_ticks) or nullptr: use `tick`
+  unsigned int* tick_ctr;    // CTAs of this launch that have read it (stage_tables_and_tick)
   int64_t N;
   int32_t actions_dtype, rewards_dtype;
 };
@@ -102,7 +103,8 @@ struct ResetParams {
   const uint8_t* mask;
   const uint32_t* inj_reset;
   uint64_t tick;
-  const uint64_t* tick_dev;
+  uint64_t* tick_dev;
+  unsigned int* tick_ctr;
   int64_t N;
 };
 
@@ -138,16 +140,13 @@ struct ActParams {
   int32_t* out;
   const uint32_t* inj_act;
   uint64_t tick;
-  const uint64_t* tick_dev;
+  uint64_t* tick_dev;
+  unsigned int* tick_ctr;
   int64_t N;
 };
 
 // ------------------------------------------------------------------------------------------ kernels
-// The launch tick of a Philox stream: a kernel parameter, or -- with device-resident ticks, which is what makes a
-// launch replayable inside a CUDA graph -- the counter in device memory that k_advance_tick bumps after every launch.
-template <typename P>
-__device__ __forceinline__ uint64_t launch_tick(const P& p) { return p.tick_dev ? __ldg(p.tick_dev) : p.tick; }
-
+// N == 0 / zero-step calls still consume ticks: advance the device-resident counter without a kernel body to do it
 __global__ void k_advance_tick(uint64_t* tick, uint64_t n) { *tick += n; }
 
 __device__ __forceinline__ uint32_t role_actions_rt(const DevConfig& c, uint32_t is_imp) {
@@ -158,13 +157,13 @@ __device__ __forceinline__ uint32_t role_actions_rt(const DevConfig& c, uint32_t
 
 __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ ResetParams p) {
   __shared__ GridTables tb;
-  stage_tables(p.c, tb);
+  stage_tables_and_tick(p.c, tb, p.tick, p.tick_dev, p.tick_ctr);
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (e >= p.N) return;
   if (p.mask && !p.mask[e]) return;
   EnvState s;
   WordStream ws;
-  ws.init(p.c, p.inj_reset ? p.inj_reset + e * (p.c.nI + p.c.A + p.c.J) : nullptr, (uint32_t)e, launch_tick(p), P_RESET);
+  ws.init(p.c, p.inj_reset ? p.inj_reset + e * (p.c.nI + p.c.A + p.c.J) : nullptr, (uint32_t)e, tb.tick, P_RESET);
   reset_env(p.c, tb, s, ws);
   store_state(p.st, e, s, true);
 }
@@ -241,7 +240,7 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
   uint64_t acts = pack_actions(in, A, ok);
   if (p.actions == nullptr) {  // fused random policy == env.step(env.sample_actions()), base.py:326-330
     WordStream wa;
-    wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, launch_tick(p), P_ACT_FUSED);
+    wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, tb.tick, P_ACT_FUSED);
     for (int i = 0; i < A; ++i)
       acts |= (uint64_t)bounded(wa.word(i), n_role_actions<VARIANT>(c, (s.imp >> i) & 1u)) << (8 * i);
   } else {
@@ -256,7 +255,7 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
     return;
   }
   WordStream ws;
-  ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, launch_tick(p), P_STEP);
+  ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, tb.tick, P_STEP);
   step_env<VARIANT, TA, TJ>(c, tb, s, acts, ws, r);
   stepped = true;
   finished = r.done || r.trunc;
@@ -325,7 +324,7 @@ __device__ __forceinline__ void finish_one(const StepParams& p, const GridTables
   if (stepped) {
     if (finished && c.auto_reset) {  // SURVEY.md A.7; train.py:419-445 does this on the host
       WordStream wr;
-      wr.init(c, p.inj_reset ? p.inj_reset + e * (c.nI + c.A + c.J) : nullptr, (uint32_t)e, launch_tick(p), P_AUTORESET);
+      wr.init(c, p.inj_reset ? p.inj_reset + e * (c.nI + c.A + c.J) : nullptr, (uint32_t)e, tb.tick, P_AUTORESET);
       reset_env(c, tb, s, wr);
       store_state(p.st, e, s, true);
     } else {
@@ -339,7 +338,7 @@ __device__ __forceinline__ void finish_one(const StepParams& p, const GridTables
 template <int VARIANT, bool ENCODE, int TA = 0, int TJ = 0>
 __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepParams p) {
   __shared__ GridTables tb;
-  stage_tables(p.c, tb);
+  stage_tables_and_tick(p.c, tb, p.tick, p.tick_dev, p.tick_ctr);
   const int lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t e0 = e - lane;
@@ -419,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, kFlatMinCtas) k_step_flat(const __gr
   const bool have = e < p.N;
   StepInput in;
   load_input(p, e, have, in);  // in flight while the tables and the row prefill are set up
-  stage_tables(p.c, tb);
+  stage_tables_and_tick(p.c, tb, p.tick, p.tick_dev, p.tick_ctr);
   if (e0 >= p.N) return;  // whole warp
   const int cnt = p.N - e0 < 32 ? (int)(p.N - e0) : 32;
   uint8_t* blk = dyn_smem + (size_t)warp * L.per_warp;
@@ -466,7 +465,8 @@ struct RolloutParams {
   unsigned long long* stats;
   double* reward_sums;  // [N][A] or nullptr: sum over the rollout of each agent index's rewards
   uint64_t tick0;
-  const uint64_t* tick_dev;
+  uint64_t* tick_dev;
+  unsigned int* tick_ctr;
   int64_t N;
   int32_t n_steps;
 };
@@ -474,7 +474,7 @@ struct RolloutParams {
 template <int VARIANT, int TA = 0, int TJ = 0>
 __global__ void __launch_bounds__(kThreads) k_rollout(const __grid_constant__ RolloutParams p) {
   __shared__ GridTables tb;
-  stage_tables(p.c, tb);
+  stage_tables_and_tick(p.c, tb, p.tick0, p.tick_dev, p.tick_ctr, (uint64_t)p.n_steps);
   const DevConfig& c = p.c;
   const int A = TA ? TA : c.A, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kThreads) k_rollout(const __grid_constant__ Ro
   uint32_t acc[SUS_N_STATS];
 #pragma unroll
   for (int k = 0; k < SUS_N_STATS; ++k) acc[k] = 0;
-  const uint64_t tick0 = p.tick_dev ? __ldg(p.tick_dev) : p.tick0;
+  const uint64_t tick0 = tb.tick;
   for (int t = 0; t < p.n_steps; ++t) {
     const uint64_t tick = tick0 + (uint64_t)t;
     if (have) {
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_tma(const __grid_
                                                           const __grid_constant__ TileLayout L) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ GridTables tb;
-  stage_tables(p.c, tb);
+  stage_tables_and_tick(p.c, tb, p.tick, p.tick_dev, p.tick_ctr);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int A = p.c.A;
   WarpEmitter em;
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_step_ws(const __grid_co
                                                                   const __grid_constant__ WsLayout L) {
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ GridTables tb;
-  stage_tables(p.c, tb);
+  stage_tables_and_tick(p.c, tb, p.tick, p.tick_dev, p.tick_ctr);
   const DevConfig& c = p.c;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int CW = L.compute_warps, A = c.A, R = p.enc.sp_floats, F = p.enc.ns_floats;
@@ -807,12 +807,15 @@ __global__ void __launch_bounds__(kThreads) k_sample_actions(const __grid_consta
   // each warp's 32 x A action words are contiguous in [N][A]: stage them in shared memory and write them with
   // lane-contiguous 4-byte stores (A strided stores per lane cost A x the store sectors)
   __shared__ int32_t stage[kThreads / 32][32 * SUS_MAX_AGENTS];
+  __shared__ uint64_t tick;
+  if (threadIdx.x == 0) tick = fetch_launch_tick(p.tick, p.tick_dev, p.tick_ctr, 1);
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, A = p.c.A;
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x, e0 = e - lane;
   if (e < p.N) {
     const uint32_t imp = (p.st.aux[e].x >> 8) & 0xff;
     WordStream wa;
-    wa.init(p.c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, launch_tick(p), P_ACT);
+    wa.init(p.c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, tick, P_ACT);
     for (int i = 0; i < A; ++i)  // base.py:326-330 (R6): dead agents are sampled too
       stage[warp][lane * A + i] = (int32_t)bounded(wa.word(i), role_actions_rt(p.c, (imp >> i) & 1u));
   }
@@ -1352,14 +1355,19 @@ struct SusEnv {
   double* ret;       // [A][N] + 2 trailing sums, allocated by sus_env_track_returns
   double gamma;
   uint64_t step_tick, reset_epoch, act_epoch;
-  uint64_t* dev_ticks;  // [3] = {step_tick, reset_epoch, act_epoch} in device memory once sus_env_device_ticks enabled them
+  uint64_t* dev_ticks;  // [3] = {step_tick, reset_epoch, act_epoch} in device memory once sus_env_device_ticks enabled them,
+                        // followed by three 32-bit CTA counters (see fetch_launch_tick)
   const uint32_t *inj_step, *inj_reset, *inj_act;
 };
 
 enum { TICK_STEP = 0, TICK_RESET = 1, TICK_ACT = 2 };
 
 namespace {
-// device-resident ticks: the counter a launch read is bumped by a one-thread kernel right behind it on the same stream
+inline unsigned int* tick_counter(SusEnv* e, int which) {
+  return e->dev_ticks ? reinterpret_cast<unsigned int*>(e->dev_ticks + 3) + which : nullptr;
+}
+
+// device-resident ticks: a call that launches no kernel (empty batch, zero steps) still consumes its ticks
 int advance_tick(SusEnv* e, int which, uint64_t n, cudaStream_t st) {
   if (!e->dev_ticks || n == 0) return SUS_OK;
   k_advance_tick<<<1, 1, 0, st>>>(e->dev_ticks + which, n);
@@ -1450,23 +1458,21 @@ int sus_env_reset(sus_env_t e, const uint8_t* mask, void* stream) {
   DeviceGuard g(e->device);
   ResetParams p;
   p.c = e->dc; p.st = e->st; p.mask = mask; p.inj_reset = e->inj_reset; p.tick = e->reset_epoch++; p.N = e->N;
-  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_RESET : nullptr;
+  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_RESET : nullptr; p.tick_ctr = tick_counter(e, TICK_RESET);
   e->inj_reset = nullptr;
-  if (e->N > 0) {
-    k_reset<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
-    if (int rc = after_launch("k_reset")) return rc;
-  }
-  return advance_tick(e, TICK_RESET, 1, (cudaStream_t)stream);
+  if (e->N == 0) return advance_tick(e, TICK_RESET, 1, (cudaStream_t)stream);
+  k_reset<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
+  return after_launch("k_reset");
 }
 
 static int step_launch(sus_env_t e, const SusStepIO* io, void* stream);
 
 int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
   if (!e || !io) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
-  const uint64_t before = e->step_tick;
   if (int rc = step_launch(e, io, stream)) return rc;
+  if (e->N > 0) return SUS_OK;  // (the kernel advanced a device-resident tick itself)
   DeviceGuard g(e->device);
-  return advance_tick(e, TICK_STEP, e->step_tick - before, (cudaStream_t)stream);  // (no tick was taken on an argument error)
+  return advance_tick(e, TICK_STEP, 1, (cudaStream_t)stream);
 }
 
 static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
@@ -1488,7 +1494,7 @@ static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
   p.metrics = reinterpret_cast<long long*>(io->metrics); p.imposters = io->imposters; p.spatial = io->spatial; p.non_spatial = io->non_spatial;
   p.inj_step = e->inj_step; p.inj_reset = e->inj_reset; p.inj_act = e->inj_act;
   p.stats = e->stats; p.err = e->err; p.tick = e->step_tick++; p.N = e->N;
-  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_STEP : nullptr;
+  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_STEP : nullptr; p.tick_ctr = tick_counter(e, TICK_STEP);
   p.ret = e->ret; p.ret_sums = e->ret ? e->ret + (size_t)e->N * p.c.A : nullptr; p.gamma = e->gamma;
   e->inj_step = e->inj_reset = e->inj_act = nullptr;
   if (e->N == 0) return SUS_OK;
@@ -1600,7 +1606,7 @@ int sus_env_rollout(sus_env_t e, int32_t n_steps, double* reward_sums, void* str
   DeviceGuard g(e->device);
   RolloutParams p;
   p.c = e->dc; p.st = e->st; p.stats = e->stats; p.reward_sums = reward_sums; p.tick0 = e->step_tick; p.N = e->N;
-  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_STEP : nullptr;
+  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_STEP : nullptr; p.tick_ctr = tick_counter(e, TICK_STEP);
   p.n_steps = n_steps;
   e->step_tick += (uint64_t)n_steps;
   if (e->N == 0 || n_steps == 0) return advance_tick(e, TICK_STEP, (uint64_t)n_steps, (cudaStream_t)stream);
@@ -1621,8 +1627,7 @@ int sus_env_rollout(sus_env_t e, int32_t n_steps, double* reward_sums, void* str
       break;
   }
 #undef SUS_LAUNCH_ROLLOUT
-  if (int rc = after_launch("k_rollout")) return rc;
-  return advance_tick(e, TICK_STEP, (uint64_t)n_steps, st);
+  return after_launch("k_rollout");
 }
 
 int sus_env_check_actions(sus_env_t e, void* stream) {
@@ -1645,11 +1650,10 @@ int sus_env_sample_actions(sus_env_t e, int32_t* out, void* stream) {
   if (!out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   ActParams p;
   p.c = e->dc; p.st = e->st; p.out = out; p.inj_act = e->inj_act; p.tick = e->act_epoch++; p.N = e->N;
-  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_ACT : nullptr;
+  p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_ACT : nullptr; p.tick_ctr = tick_counter(e, TICK_ACT);
   e->inj_act = nullptr;
   k_sample_actions<<<grid_for(e->N), kThreads, 0, (cudaStream_t)stream>>>(p);
-  if (int rc = after_launch("k_sample_actions")) return rc;
-  return advance_tick(e, TICK_ACT, 1, (cudaStream_t)stream);
+  return after_launch("k_sample_actions");
 }
 
 int sus_env_export_flat(sus_env_t e, int32_t dtype, void* out, void* stream) {
@@ -1855,8 +1859,8 @@ int sus_env_device_ticks(sus_env_t e, int32_t enable, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (enable && !e->dev_ticks) {
     uint64_t* d = nullptr;
-    SUS_CUDA(cudaMalloc(&d, 3 * sizeof(uint64_t)));
-    const uint64_t h[3] = {e->step_tick, e->reset_epoch, e->act_epoch};
+    SUS_CUDA(cudaMalloc(&d, 5 * sizeof(uint64_t)));  // three ticks + three 32-bit CTA counters
+    const uint64_t h[5] = {e->step_tick, e->reset_epoch, e->act_epoch, 0, 0};
     SUS_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
     SUS_CUDA(cudaStreamSynchronize(st));
     e->dev_ticks = d;

@@ -33,11 +33,36 @@ struct DevConfig {
 struct GridTables {
   uint32_t valid_bits[8];
   uint8_t cell_code[84];
+  uint64_t tick;  // the launch's Philox tick (kernels that draw; see stage_tables_and_tick)
 };
 
 __device__ __forceinline__ void stage_tables(const DevConfig& c, GridTables& t) {
   for (int i = threadIdx.x; i < 8; i += blockDim.x) t.valid_bits[i] = c.valid_bits[i];
   for (int i = threadIdx.x; i < 84; i += blockDim.x) t.cell_code[i] = c.cell_code[i];
+  __syncthreads();
+}
+
+// The tick that keys a launch's draws: a kernel parameter, or -- device-resident ticks (sus_env_device_ticks), which is
+// what makes a launch replayable inside a CUDA graph -- a counter in device memory.  Thread 0 of every CTA reads it once
+// and counts the CTA in; the CTA that completes the count (every CTA of the launch has read the tick by then) advances
+// the counter by `n_ticks` for the next launch and re-arms the count.  No extra launch, nothing at kernel exit.
+__device__ __forceinline__ uint64_t fetch_launch_tick(uint64_t host_tick, uint64_t* tick_dev, unsigned int* tick_ctr,
+                                                      uint64_t n_ticks) {
+  if (!tick_dev) return host_tick;
+  const uint64_t tick = *reinterpret_cast<volatile uint64_t*>(tick_dev);
+  __threadfence();
+  if (atomicAdd(tick_ctr, 1u) == gridDim.x - 1) {
+    *reinterpret_cast<volatile uint64_t*>(tick_dev) = tick + n_ticks;
+    *reinterpret_cast<volatile unsigned int*>(tick_ctr) = 0u;
+    __threadfence();
+  }
+  return tick;
+}
+__device__ __forceinline__ void stage_tables_and_tick(const DevConfig& c, GridTables& t, uint64_t host_tick,
+                                                      uint64_t* tick_dev, unsigned int* tick_ctr, uint64_t n_ticks = 1) {
+  for (int i = threadIdx.x; i < 8; i += blockDim.x) t.valid_bits[i] = c.valid_bits[i];
+  for (int i = threadIdx.x; i < 84; i += blockDim.x) t.cell_code[i] = c.cell_code[i];
+  if (threadIdx.x == 0) t.tick = fetch_launch_tick(host_tick, tick_dev, tick_ctr, n_ticks);
   __syncthreads();
 }
 
