@@ -28,11 +28,13 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 20)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--check-every", type=int, default=100)
-    ap.add_argument("--config", choices=["global", "flat"], default="global")
+    ap.add_argument("--config", choices=["global", "flat", "tagging"], default="global")
     a = ap.parse_args()
     N, T = a.envs, a.steps
     if a.config == "flat":
         return soak_flat(N, T, a.check_every)
+    if a.config == "tagging":
+        return soak_tagging(N, T, a.check_every)
     cfg = oracle.default_config("base", n_crew=4, n_jobs=5)
     env = S.BatchedFourRoomEnv(1, 4, 5, num_envs=N, seed=99, device="cuda:0")
     feat = S.GlobalFeaturizer(env)
@@ -99,6 +101,36 @@ def soak_flat(N, T, check_every):
     print(json.dumps({"config": "cfg4-alt ITG 1v4 walled + Flat-98 (k_step_flat)", "envs": N, "steps": T, "env_steps": N * T,
                       "full_state_and_feature_comparisons": checks, "finished_trajectories": stats["episodes"], "stats": stats,
                       "wall_s": round(time.time() - t0, 1), "result": "identical"}))
+
+
+def soak_tagging(N, T, check_every):
+    """cfg3 (FourRoomEnvWithTagging 1v2, 5 jobs; BASELINE configs[2]), step only, explicit sample_actions + step."""
+    from tests.cases import CASES
+    from tests.util import make_cuda_env
+
+    cfg = CASES["cfg3_tagging_1v2"]
+    env = make_cuda_env(cfg, N, seed=99)
+    orc = oracle.OracleEnv(cfg, N, seed=99)
+    oracle.set_threads(os.cpu_count() or 1)
+    assert np.array_equal(env.reset()[0].cpu().numpy().astype(np.int64), orc.reset())
+    t0, out, checks = time.time(), None, 0
+    for t in range(1, T + 1):
+        acts = env.sample_actions()
+        nf, r, d, tr, _ = env.step(acts)
+        oa = orc.sample_actions()
+        out = orc.step(oa, want_flat=False, want_metrics=False, out=out)
+        if t % check_every == 0 or t == T:
+            assert np.array_equal(acts.cpu().numpy(), oa), f"sampled actions differ at step {t}"
+            assert np.array_equal(env.flat_states(torch.int64).cpu().numpy(), orc.flat_states()), f"states differ at step {t}"
+            assert np.array_equal(env.episode_stats().cpu().numpy(), orc.stats()), f"episode stats differ at step {t}"
+            assert np.array_equal(r.cpu().numpy(), out["rewards"].astype(np.float32)), f"rewards differ at step {t}"
+            assert np.array_equal(d.cpu().numpy(), out["done"] != 0) and np.array_equal(tr.cpu().numpy(), out["trunc"] != 0)
+            checks += 1
+    env.check_actions()
+    stats = dict(zip(S.STAT_KEYS, [int(x) for x in orc.stats()]))
+    print(json.dumps({"config": "cfg3 FourRoomEnvWithTagging 1v2, 5 jobs, step only (sample_actions + step)", "envs": N, "steps": T,
+                      "env_steps": N * T, "full_state_comparisons": checks, "finished_trajectories": stats["episodes"],
+                      "stats": stats, "wall_s": round(time.time() - t0, 1), "result": "identical"}))
 
 
 if __name__ == "__main__":
