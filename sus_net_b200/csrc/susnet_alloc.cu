@@ -79,6 +79,11 @@ extern "C" {
 int sus_alloc_compressible(int device, uint64_t bytes, void** ptr, uint64_t* allocated) {
   if (!ptr || bytes == 0) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "sus_alloc_compressible: NULL ptr or zero size");
   *ptr = nullptr;
+  struct Restore {  // leave the caller's current device as it was
+    int prev = -1;
+    Restore() { cudaGetDevice(&prev); }
+    ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+  } restore;
   if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess)
     return sus_internal_fail(SUS_ERR_CUDA, "sus_alloc_compressible: cannot select the CUDA device");
   const Driver& d = driver();
