@@ -814,10 +814,21 @@ __global__ void __launch_bounds__(kThreads) k_sample_actions(const __grid_consta
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x, e0 = e - lane;
   if (e < p.N) {
     const uint32_t imp = (p.st.aux[e].x >> 8) & 0xff;
-    WordStream wa;
-    wa.init(p.c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, tick, P_ACT);
-    for (int i = 0; i < A; ++i)  // base.py:326-330 (R6): dead agents are sampled too
-      stage[warp][lane * A + i] = (int32_t)bounded(wa.word(i), role_actions_rt(p.c, (imp >> i) & 1u));
+    uint32_t w[SUS_MAX_AGENTS];  // word i of the (env, act epoch, P_ACT) stream
+    if (p.inj_act) {
+#pragma unroll
+      for (int i = 0; i < SUS_MAX_AGENTS; ++i) w[i] = i < A ? p.inj_act[e * A + i] : 0u;
+    } else {  // == WordStream::word(0..7), with the two blocks' rounds interleaved
+      const uint32_t env_id = p.c.env_id_base + (uint32_t)e;
+      uint4 a = make_uint4(env_id, (uint32_t)tick, (uint32_t)(tick >> 32), P_ACT), b = a;
+      b.w |= 1u << 8;
+      if (A > 4) philox4x32_10_x2(a, b, p.c.seed_lo, p.c.seed_hi);
+      else a = philox4x32_10(a, p.c.seed_lo, p.c.seed_hi);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    }
+#pragma unroll
+    for (int i = 0; i < SUS_MAX_AGENTS; ++i)  // base.py:326-330 (R6): dead agents are sampled too
+      if (i < A) stage[warp][lane * A + i] = (int32_t)bounded(w[i], role_actions_rt(p.c, (imp >> i) & 1u));
   }
   __syncwarp();
   const int64_t rem = p.N - e0;

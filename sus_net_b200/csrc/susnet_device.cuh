@@ -133,6 +133,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint32_t k0, uint32_t 
   return ctr;
 }
 
+// two independent blocks in one loop: the two 10-round dependency chains interleave (k_sample_actions with A > 4)
+__device__ __forceinline__ void philox4x32_10_x2(uint4& a, uint4& b, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t ah0 = __umulhi(0xD2511F53u, a.x), al0 = 0xD2511F53u * a.x, ah1 = __umulhi(0xCD9E8D57u, a.z), al1 = 0xCD9E8D57u * a.z;
+    const uint32_t bh0 = __umulhi(0xD2511F53u, b.x), bl0 = 0xD2511F53u * b.x, bh1 = __umulhi(0xCD9E8D57u, b.z), bl1 = 0xCD9E8D57u * b.z;
+    a = make_uint4(ah1 ^ a.y ^ k0, al1, ah0 ^ a.w ^ k1, al0);
+    b = make_uint4(bh1 ^ b.y ^ k0, bl1, bh0 ^ b.w ^ k1, bl0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
 __device__ __forceinline__ uint32_t bounded(uint32_t u, uint32_t k) { return __umulhi(u, k); }
 
 // One logical word stream (env, tick, purpose): either injected raw words (parity mode) or Philox,
