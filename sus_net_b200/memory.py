@@ -24,10 +24,12 @@ class _Block:
     that exports __cuda_array_interface__ until the storage dies) and the memory is unmapped when the last one goes."""
 
     def __init__(self, lib, ptr, shape):
-        self._lib, self._ptr = lib, ptr
+        self._lib, self._ptr, self._pid = lib, ptr, os.getpid()
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
 
     def __del__(self):
+        if os.getpid() != self._pid:  # a forked child (e.g. a DataLoader worker) must not touch the parent's CUDA context
+            return
         try:
             if torch.cuda.is_current_stream_capturing():
                 _deferred.append((self._lib, self._ptr))  # freeing synchronises the device: not inside a graph capture
