@@ -12,10 +12,11 @@ auto-reset, Global feature tensors of the state the next action is taken from).
 
 Numbers on the JSON line
   value     whole-job env-steps/s with state and actions resident in HBM (CUDA events, max over ranks)
-  e2e       the same work driven through the public Python API with HOST buffers: per step the actions (uint8
-            role-list indices) come from pinned host memory (H2D) and rewards/dones/truncations go back to pinned
-            host memory (D2H); the
-            feature tensors stay on the device, where the Q-network consumes them
+  e2e       the same work driven through the public Python API with HOST buffers (sus_net_b200.HostStepper): per step
+            the actions come from pinned host memory (H2D) and rewards/dones/truncations go back to pinned host
+            memory (D2H) in the compact host protocol (bit-packed role-list indices in, reward codes + done/trunc
+            bits out; `e2e.dense_protocol` = the same with uint8 actions / float32 rewards); the feature tensors
+            stay on the device, where the Q-network consumes them
   roofline  achieved = 2650 algorithmic bytes per env-step x envs per launch / mean duration of the
             fused step+encode kernel, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.  The feature
             tensors live in L2-compressible memory, so the DRAM bytes per launch (`traffic`, from the ncu capture in
@@ -370,43 +371,59 @@ def run_b200_arm(args):
     e2e = None
     if not args.no_e2e:
         # record a valid action stream (roles change at every auto-reset, so actions are recorded from a shadow run of
-        # the same deterministic trajectory: same seed and env ids => identical states)
+        # the same deterministic trajectory: same seed and env ids => identical states), in both wire formats
         rec = make_env()
         rec.reset()
-        host_actions = torch.empty((W + K, N, A), dtype=torch.uint8).pin_memory()  # role-list indices < 256
+        cp = rec.compact
+        host_packed = torch.empty((W + K, N, cp.action_bytes), dtype=torch.uint8).pin_memory()
+        host_dense = torch.empty((W + K, N, A), dtype=torch.uint8).pin_memory()
         for k in range(W + K):
             a = rec.sample_actions()
-            host_actions[k].copy_(a.to(torch.uint8), non_blocking=True)
+            host_packed[k].copy_(cp.pack_actions(a), non_blocking=True)
+            host_dense[k].copy_(a.to(torch.uint8), non_blocking=True)
             rec.step(a, featurizer=feat)
         torch.cuda.synchronize(dev)
+        stats_shadow = rec.episode_stats().clone()
         del rec
-        env = make_env()
-        env.reset()
-        torch.cuda.synchronize(dev)
-        stepper = S.HostStepper(env, featurizer=feat)   # public API: 3 streams x 2 slots, H2D | kernel | D2H overlap
-        for k in range(W):
-            stepper.step(host_actions[k])
-        stepper.drain()
-        barrier()
-        s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s4.record()
-        for k in range(W, W + K):
-            slot = stepper.step(host_actions[k])
-        stepper.drain()
-        e4.record()
-        barrier()
-        h_rewards, h_done, h_trunc = stepper.wait(slot)
-        env.check_actions()  # every replayed action was valid for its agent's role
-        e2e_ms = max_over_ranks(s4.elapsed_time(e4), device=dev)
-        # the same chain on ONE stream (no overlap between the copies and the kernel), for reference
+
+        def run_stepper(protocol, host_actions):
+            env = make_env()
+            env.reset()
+            torch.cuda.synchronize(dev)
+            stepper = S.HostStepper(env, featurizer=feat, protocol=protocol)  # public API: 3 streams x 2 slots
+            for k in range(W):
+                stepper.step(host_actions[k])
+            stepper.drain()
+            barrier()
+            s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s4.record()
+            for k in range(W, W + K):
+                slot = stepper.step(host_actions[k])
+            stepper.drain()
+            e4.record()
+            barrier()
+            res = stepper.wait(slot)
+            env.check_actions()  # every replayed action was valid for its agent's role
+            ok = bool(torch.equal(env.episode_stats(), stats_shadow))  # the host-driven run walked the recorded trajectory
+            ms = max_over_ranks(s4.elapsed_time(e4), device=dev)
+            return ms, stepper.h2d_bytes_per_step, stepper.d2h_bytes_per_step, res, ok
+
+        e2e_ms, h2d, d2h, res, same = run_stepper("compact", host_packed)
+        t0 = time.perf_counter()
+        rewards_last = res.rewards  # lazy host decode of the last step's records (numpy, outside the timed region)
+        decode_s = time.perf_counter() - t0
+        dense_ms, dense_h2d, dense_d2h, _, same_dense = run_stepper("dense", host_dense)
+        # the compact chain on ONE stream (no overlap between the copies and the kernel), for reference
         seq = make_env()
         seq.reset()
-        d_actions = torch.empty((N, A), dtype=torch.uint8, device=dev)
+        d_actions = torch.empty((N, cp.action_bytes), dtype=torch.uint8, device=dev)
+        d_res = torch.empty((N, cp.result_bytes), dtype=torch.uint8, device=dev)
+        h_res = torch.empty((N, cp.result_bytes), dtype=torch.uint8).pin_memory()
 
         def seq_step(k):
-            d_actions.copy_(host_actions[k], non_blocking=True)
-            _nf, r, d, t, _ = seq.step(d_actions, featurizer=feat)
-            h_rewards.copy_(r, non_blocking=True); h_done.copy_(d, non_blocking=True); h_trunc.copy_(t, non_blocking=True)
+            d_actions.copy_(host_packed[k], non_blocking=True)
+            seq.step(d_actions, featurizer=feat, packed_actions=True, packed_out=d_res)
+            h_res.copy_(d_res, non_blocking=True)
 
         for k in range(W):
             seq_step(k)
@@ -419,14 +436,20 @@ def run_b200_arm(args):
         barrier()
         seq_ms = max_over_ranks(s5.elapsed_time(e5), device=dev)
         e2e = {"value": world * N * K / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": world * stepper.h2d_bytes_per_step,
-               "d2h_bytes_per_step": world * stepper.d2h_bytes_per_step,
+               "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h,
+               "protocol": f"compact: {cp.action_bytes} B of bit-packed actions in, {cp.result_bytes} B of reward codes + done/trunc "
+                           f"bits out per env-step (sus_net_b200/compact.py; decoded rewards are bit-equal to the float64 rewards)",
                "single_stream_value": world * N * K / (seq_ms * 1e-3),
-               "note": "sus_net_b200.HostStepper: uint8 actions H2D from pinned host memory, fused step+encode, rewards f32 "
-                       "+ done + truncated D2H to pinned host memory every step (3 streams, 2 slots); feature tensors stay "
-                       "in HBM for the Q-network; no sampler kernel in this loop (the actions arrive from the host), which "
-                       "is why it can exceed `value`"}
-        del env, seq
+               "dense_protocol": {"value": world * N * K / (dense_ms * 1e-3), "h2d_bytes_per_step": world * dense_h2d,
+                                  "d2h_bytes_per_step": world * dense_d2h,
+                                  "what": "uint8 actions in, float32 rewards + done + truncated bytes out (round 1's wire format)"},
+               "trajectory_check": bool(same and same_dense),
+               "host_decode_ms_last_step": 1e3 * decode_s, "host_decoded_reward_sum_last_step": float(rewards_last.sum()),
+               "note": "sus_net_b200.HostStepper: actions H2D from pinned host memory, fused step+encode, results D2H to pinned "
+                       "host memory every step (3 streams, 2 slots, per-slot feature tensors); feature tensors stay in HBM for "
+                       "the Q-network; no sampler kernel in this loop (the actions arrive from the host), which is why it can "
+                       "exceed `value`; the host decodes the result records lazily (not in the timed region)"}
+        del seq
 
     # ---- the one collective of the path: final episode-statistics reduce (NCCL)
     stats = reduce_episode_stats(stats_local)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SUS_ABI_VERSION 1
+#define SUS_ABI_VERSION 2
 
 #define SUS_MAX_AGENTS 8
 #define SUS_MAX_JOBS 8
@@ -47,7 +47,8 @@ enum SusError {
 /* src/environment/{base.py:102, tagging.py:9, pred_prey.py:20} */
 enum SusVariant { SUS_VARIANT_BASE = 0, SUS_VARIANT_TAGGING = 1, SUS_VARIANT_TRAINING_GROUND = 2 };
 
-enum SusDtype { SUS_U8 = 0, SUS_I32 = 1, SUS_I64 = 2, SUS_F32 = 3, SUS_F64 = 4 };
+enum SusDtype { SUS_U8 = 0, SUS_I32 = 1, SUS_I64 = 2, SUS_F32 = 3, SUS_F64 = 4,
+                SUS_PACKED = 5 /* actions only: bit-packed records of the compact host protocol, see SusCompactLayout */ };
 
 /* src/metrics.py:7-32 -- the counters the env touches (base.py:366,508,522,531; tagging.py:199,201;
  * base.py:433,444; pred_prey.py:90,96). */
@@ -152,7 +153,31 @@ typedef struct SusStepIO {
                               taken from (post auto-reset), written to spatial / non_spatial below */
   float *spatial;          /* [views_s][N][spatial_floats]  */
   float *non_spatial;      /* [views_n][N][non_spatial_floats] */
+  uint8_t *packed_out;     /* [N][result_bytes] compact result records (SusCompactLayout) INSTEAD of rewards / done /
+                              truncated, which must then be NULL: what a host consumer pulls over PCIe per step */
 } SusStepIO;
+
+/* Compact host protocol (no reference analogue: the reference's step() hands numpy arrays to a caller in the same
+ * process, train.py:383-399; here every byte of a step's actions and results crosses PCIe).  A step's reward of an
+ * agent is one of a handful of values -- the event it was last assigned (none / kill / fix / sabotage, base.py:511-532),
+ * plus the team reward (win +-game_end_reward, base.py:428-446; vote +-vote_reward, tagging.py:196), negated for agent
+ * indices < n_imposters (base.py:559), or dead_penalty (base.py:562), with zeros replaced by time_step_reward
+ * (base.py:389-390) -- so it travels as a small CODE and the host decodes it through the float64 table of
+ * sus_reward_lut(), which is computed with the same float64 operation sequence as the kernel: decoding is bit-exact
+ * for arbitrary reward constants.
+ *   packed action record, action_bytes per env, little-endian bit order: agent i's role-list index in bits
+ *     [i*action_bits, (i+1)*action_bits)                                   (SusStepIO.actions with SUS_PACKED)
+ *   packed result record, result_bytes per env: agent i's reward code in bits [i*reward_bits, (i+1)*reward_bits),
+ *     done in bit A*reward_bits, truncated in bit A*reward_bits + 1          (SusStepIO.packed_out)
+ *   code = dead ? n_live_codes : event + 4 * (win + 3 * vote); event 0 none, 1 kill, 2 fix, 3 sabotage; win 0 none,
+ *     1 crew, 2 imposters; vote 0 none, 1 crew member ejected, 2 imposter ejected.  An env whose actions were rejected
+ *     (SUS_ERR_INVALID_ACTION) reports the all-ones code for every agent (decodes to NaN) with done = truncated = 0. */
+typedef struct SusCompactLayout {
+  int32_t action_bits, action_bytes;
+  int32_t reward_bits, result_bytes;
+  int32_t n_codes;      /* valid codes are 0 .. n_codes-1; n_codes-1 = dead */
+  int32_t invalid_code; /* (1 << reward_bits) - 1 */
+} SusCompactLayout;
 
 typedef struct SusEnv *sus_env_t;
 
@@ -164,6 +189,11 @@ const char *sus_last_error(void); /* host string, valid until the thread's next 
 int sus_flat_state_size(const SusConfig *cfg);
 int sus_n_role_actions(const SusConfig *cfg, int is_imposter);
 int sus_encode_shape(const SusConfig *cfg, const SusEncodeSpec *spec, SusEncodeShape *out /*host*/);
+/* Record geometry of the compact host protocol for a config.  Host call. */
+int sus_compact_layout(const SusConfig *cfg, SusCompactLayout *out /*host*/);
+/* Decode table of the reward codes: out[i * (invalid_code + 1) + code] = float64 reward of agent index i for `code`
+ * (NaN for codes >= n_codes); A * (invalid_code + 1) doubles.  Host call, no GPU work. */
+int sus_reward_lut(const SusConfig *cfg, double *out /*host*/);
 
 /* FourRoomEnv.__init__ & co. (base.py:103-228): validates like _validate_init_args (base.py:243-249,
  * pred_prey.py:75-76), builds the wall grid, allocates the structure-of-arrays state for num_envs envs on

@@ -8,10 +8,10 @@ LIB_PATH = os.environ.get("SUSNET_B200_LIB") or os.path.join(HERE, "libsusnet_b2
 
 SUS_OK, SUS_ERR_INVALID_ARGUMENT, SUS_ERR_UNSUPPORTED, SUS_ERR_CUDA, SUS_ERR_INVALID_ACTION = 0, -1, -2, -3, -4
 VARIANT_BASE, VARIANT_TAGGING, VARIANT_TRAINING_GROUND = 0, 1, 2
-U8, I32, I64, F32, F64 = 0, 1, 2, 3, 4
+U8, I32, I64, F32, F64, PACKED = 0, 1, 2, 3, 4, 5
 ENCODE_NONE, ENCODE_GLOBAL, ENCODE_PERSPECTIVE, ENCODE_FLAT = 0, 1, 2, 3
 MAX_AGENTS, MAX_JOBS, N_METRICS, N_STATS, MAX_FLAT_COMPONENTS = 8, 8, 8, 10, 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTED_SYMBOLS = (
     "sus_abi_version", "sus_last_error", "sus_flat_state_size", "sus_n_role_actions", "sus_encode_shape",
@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "sus_env_export_metrics", "sus_env_encode", "sus_encode_from_flat", "sus_env_stats", "sus_env_clear_stats",
     "sus_env_get_ticks", "sus_env_set_ticks", "sus_env_state_arrays", "sus_env_debug_inject_words",
     "sus_launch_count", "sus_replay_push", "sus_env_rollout", "sus_env_track_returns", "sus_env_return_sums",
-    "sus_env_device_ticks", "sus_alloc_compressible", "sus_free_compressible",
+    "sus_env_device_ticks", "sus_alloc_compressible", "sus_free_compressible", "sus_compact_layout", "sus_reward_lut",
 )
 
 
@@ -50,8 +50,13 @@ class SusStepIO(C.Structure):
         ("actions", C.c_void_p), ("actions_dtype", C.c_int32), ("rewards_dtype", C.c_int32), ("rewards", C.c_void_p),
         ("done", C.c_void_p), ("truncated", C.c_void_p), ("actions_out", C.c_void_p), ("next_flat", C.c_void_p),
         ("metrics", C.c_void_p), ("imposters", C.c_void_p), ("encode", C.POINTER(SusEncodeSpec)), ("spatial", C.c_void_p),
-        ("non_spatial", C.c_void_p),
+        ("non_spatial", C.c_void_p), ("packed_out", C.c_void_p),
     ]
+
+
+class SusCompactLayout(C.Structure):
+    _fields_ = [("action_bits", C.c_int32), ("action_bytes", C.c_int32), ("reward_bits", C.c_int32),
+                ("result_bytes", C.c_int32), ("n_codes", C.c_int32), ("invalid_code", C.c_int32)]
 
 
 class SusReplayPush(C.Structure):
@@ -91,6 +96,8 @@ def lib():
         "sus_flat_state_size": ([C.POINTER(SusConfig)], C.c_int),
         "sus_n_role_actions": ([C.POINTER(SusConfig), C.c_int], C.c_int),
         "sus_encode_shape": ([C.POINTER(SusConfig), C.POINTER(SusEncodeSpec), C.POINTER(SusEncodeShape)], C.c_int),
+        "sus_compact_layout": ([C.POINTER(SusConfig), C.POINTER(SusCompactLayout)], C.c_int),
+        "sus_reward_lut": ([C.POINTER(SusConfig), C.POINTER(C.c_double)], C.c_int),
         "sus_env_create": ([C.POINTER(SusConfig), C.c_int, C.POINTER(vp)], C.c_int),
         "sus_env_destroy": ([vp], C.c_int),
         "sus_env_reset": ([vp, vp, vp], C.c_int),

@@ -21,6 +21,7 @@
 //   plus small export / import kernels for the reference's flatten order, k_replay_push (susnet_replay.cu) and the
 //   L2-compressible allocator the feature tensors live in (susnet_alloc.cu).
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -95,6 +96,9 @@ struct StepParams {
   unsigned int* tick_ctr;    // CTAs of this launch that have read it (stage_tables_and_tick)
   int64_t N;
   int32_t actions_dtype, rewards_dtype;
+  // compact host protocol (SusCompactLayout): packed result records instead of rewards / done / trunc
+  uint8_t* packed_out;
+  int32_t action_bits, action_bytes, reward_bits, result_bytes;
 };
 
 struct ResetParams {
@@ -168,6 +172,14 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ Rese
   store_state(p.st, e, s, true);
 }
 
+// the per-env "reward row" of a launch: float rewards [A] (f32 / f64) or one packed result record (compact host protocol)
+__device__ __forceinline__ int reward_row_bytes(const StepParams& p) {
+  return p.packed_out ? p.result_bytes : p.c.A * (p.rewards_dtype == SUS_F64 ? 8 : 4);
+}
+__device__ __forceinline__ uint8_t* reward_rows(const StepParams& p) {
+  return p.packed_out ? p.packed_out : static_cast<uint8_t*>(p.rewards);
+}
+
 // ---- everything a step reads for one env, as raw words: loaded one group ahead by the TMA kernel so the DRAM
 // latency of the state records and the action rows hides behind the previous group's work
 struct StepInput {
@@ -196,6 +208,11 @@ __device__ __forceinline__ void load_input(const StepParams& p, int64_t e, bool 
 #pragma unroll
     for (int i = 0; i < SUS_MAX_AGENTS; ++i)
       if (i < A) in.raw[i] = a[i];
+  } else if (p.actions_dtype == SUS_PACKED) {  // the record's bytes, still packed (<= 4 bytes: 8 agents x 4 bits)
+    const uint8_t* a = static_cast<const uint8_t*>(p.actions) + e * p.action_bytes;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < p.action_bytes) in.raw[i] = a[i];
   } else {
     const unsigned long long* a = static_cast<const unsigned long long*>(p.actions) + e * A;
 #pragma unroll
@@ -205,8 +222,17 @@ __device__ __forceinline__ void load_input(const StepParams& p, int64_t e, bool 
 }
 
 // one byte per agent + "some action was negative or >= 256"
-__device__ __forceinline__ uint64_t pack_actions(const StepInput& in, int A, bool& in_range) {
+__device__ __forceinline__ uint64_t pack_actions(const StepParams& p, const StepInput& in, int A, bool& in_range) {
   uint64_t acts = 0;
+  if (p.actions_dtype == SUS_PACKED) {
+    const uint32_t rec = in.raw[0] | (in.raw[1] << 8) | (in.raw[2] << 16) | (in.raw[3] << 24);
+    const uint32_t m = (1u << p.action_bits) - 1u;
+#pragma unroll
+    for (int i = 0; i < SUS_MAX_AGENTS; ++i)
+      if (i < A) acts |= (uint64_t)((rec >> (i * p.action_bits)) & m) << (8 * i);
+    in_range = true;
+    return acts;
+  }
   uint32_t oob = in.oob64;
 #pragma unroll
   for (int i = 0; i < SUS_MAX_AGENTS; ++i)
@@ -237,7 +263,7 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
   unpack_state(in, s);
   // ---- actions: role-list indices, one byte per agent
   bool ok = true;
-  uint64_t acts = pack_actions(in, A, ok);
+  uint64_t acts = pack_actions(p, in, A, ok);
   if (p.actions == nullptr) {  // fused random policy == env.step(env.sample_actions()), base.py:326-330
     WordStream wa;
     wa.init(c, p.inj_act ? p.inj_act + e * A : nullptr, (uint32_t)e, tb.tick, P_ACT_FUSED);
@@ -250,25 +276,40 @@ __device__ __forceinline__ void step_one(const StepParams& p, const GridTables& 
   }
   if (p.actions_out)
     for (int i = 0; i < A; ++i) p.actions_out[e * A + i] = (int32_t)get_byte(acts, i);
-  if (!ok) {  // reference: IndexError (base.py:381); here the env is left untouched and the error is counted
+  r = StepResult{};
+  if (!ok) {
+    // reference: IndexError (base.py:381).  Here the env is left untouched, the error is counted (sus_env_check_actions)
+    // and the step's outputs are DEFINED: NaN rewards (the all-ones reward code), done = truncated = 0, next_flat = the
+    // unchanged state
     atomicAdd(p.err, 1u);
-    return;
+  } else {
+    WordStream ws;
+    ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, tb.tick, P_STEP);
+    step_env<VARIANT, TA, TJ>(c, tb, s, acts, ws, r);
+    stepped = true;
+    finished = r.done || r.trunc;
   }
-  WordStream ws;
-  ws.init(c, p.inj_step ? p.inj_step + e * (2 * A - 1) : nullptr, (uint32_t)e, tb.tick, P_STEP);
-  step_env<VARIANT, TA, TJ>(c, tb, s, acts, ws, r);
-  stepped = true;
-  finished = r.done || r.trunc;
   r.ret_imp = r.ret_crew = 0.0;
-  if (rew_row || p.ret) {
+  if (p.packed_out && rew_row) {  // compact host protocol: reward codes + done / truncated bits in one record
+    const int rb = p.reward_bits;
+    uint64_t rec = 0;
+    for (int i = 0; i < A; ++i)
+      rec |= (uint64_t)(ok ? agent_reward_code(c, s, r, i) : (1u << rb) - 1u) << (i * rb);
+    rec |= (uint64_t)(r.done ? 1u : 0u) << (A * rb);
+    rec |= (uint64_t)(r.trunc ? 1u : 0u) << (A * rb + 1);
+    uint8_t* o = static_cast<uint8_t*>(rew_row);
+    for (int b = 0; b < p.result_bytes; ++b) o[b] = (uint8_t)(rec >> (8 * b));
+  }
+  const bool float_rewards = rew_row && !p.packed_out;
+  if (float_rewards || (p.ret && ok)) {
     double g_imp = 0.0, g_crew = 0.0;
     for (int i = 0; i < A; ++i) {
-      const double v = agent_reward<VARIANT>(c, s, r, i);
-      if (rew_row) {
+      const double v = ok ? agent_reward<VARIANT>(c, s, r, i) : __longlong_as_double(0x7ff8000000000000ll);
+      if (float_rewards) {
         if (p.rewards_dtype == SUS_F64) static_cast<double*>(rew_row)[i] = v;
         else static_cast<float*>(rew_row)[i] = (float)v;
       }
-      if (p.ret) {  // G = reward + gamma * G (train.py:386); reset to 0 when the episode ends (train.py:436)
+      if (p.ret && ok) {  // G = reward + gamma * G (train.py:386); reset to 0 when the episode ends (train.py:436)
         const double g = __dadd_rn(v, __dmul_rn(p.gamma, p.ret[(int64_t)i * p.N + e]));  // two roundings like numpy, no FMA
         if ((s.imp >> i) & 1u) g_imp += g; else g_crew += g;
         p.ret[(int64_t)i * p.N + e] = finished ? 0.0 : g;
@@ -348,8 +389,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ StepP
   StepResult r = {};
   StepInput in;
   load_input(p, e, have, in);
-  step_one<VARIANT, TA, TJ>(p, tb, e, have, in,
-                    p.rewards ? static_cast<uint8_t*>(p.rewards) + e * p.c.A * (p.rewards_dtype == SUS_F64 ? 8 : 4) : nullptr,
+  step_one<VARIANT, TA, TJ>(p, tb, e, have, in, reward_rows(p) ? reward_rows(p) + e * reward_row_bytes(p) : nullptr,
                     p.next_flat ? p.next_flat + e * p.c.S : nullptr, s, r, stepped, finished);
   finish_one(p, tb, e, lane, s, r, stepped, finished);
   if (ENCODE) {
@@ -374,6 +414,17 @@ __device__ __forceinline__ void warp_copy_words(uint32_t* __restrict__ g, const 
     done = n4 << 2;
   }
   for (int i = done + lane; i < n_words; i += 32) g[i] = s[i];
+}
+
+// Copy `n_bytes` from a warp's staging block to global memory: words where both the destination and the size allow,
+// single bytes over a ragged tail / odd destination (packed result records of a ragged or unaligned batch).  All 32 lanes.
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ g, const uint8_t* __restrict__ s, int n_bytes, int lane) {
+  if (((uint32_t)reinterpret_cast<uintptr_t>(g) & 3u) == 0) {
+    warp_copy_words(reinterpret_cast<uint32_t*>(g), reinterpret_cast<const uint32_t*>(s), n_bytes >> 2, lane);
+    for (int i = (n_bytes & ~3) + lane; i < n_bytes; i += 32) g[i] = s[i];
+  } else {
+    for (int i = lane; i < n_bytes; i += 32) g[i] = s[i];
+  }
 }
 
 // Expand a warp's staged byte rows to `n` floats at `out`: word i of the block holds floats [4i, 4i + 4).  Lane-contiguous
@@ -426,32 +477,20 @@ __global__ void __launch_bounds__(kThreads, kFlatMinCtas) k_step_flat(const __gr
     const uint32_t z = kByteRowBias * 0x01010101u;
     for (int i = lane; i < (L.row_bytes >> 4); i += 32) reinterpret_cast<uint4*>(blk)[i] = make_uint4(z, z, z, z);
   }
-  const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
+  const int rew_row = reward_row_bytes(p);
   uint8_t* rew = blk + L.rew_off;
   float* nf = reinterpret_cast<float*>(blk + L.nf_off);
   bool stepped, finished;
   EnvState s = {};
   StepResult r = {};
-  step_one<VARIANT, TA, TJ>(p, tb, e, have, in, p.rewards ? rew + lane * A * rew_elem : nullptr, p.next_flat ? nf + lane * S : nullptr,
+  step_one<VARIANT, TA, TJ>(p, tb, e, have, in, reward_rows(p) ? rew + lane * rew_row : nullptr, p.next_flat ? nf + lane * S : nullptr,
                     s, r, stepped, finished);
   finish_one(p, tb, e, lane, s, r, stepped, finished);
   __syncwarp();  // the prefill is complete before any lane sets bytes in its row
   if (have) flat_row<ByteRow>(p.c, p.enc, tb, obs_of(s), blk + lane * F);
-  const bool all_stepped = __all_sync(kFull, stepped || !have);  // (also orders the staged rows before the reads below)
-  if (all_stepped) {
-    if (p.rewards)
-      warp_copy_words(reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.rewards) + e0 * A * rew_elem),
-                      reinterpret_cast<const uint32_t*>(rew), cnt * A * rew_elem / 4, lane);
-    if (p.next_flat) warp_copy_words(reinterpret_cast<uint32_t*>(p.next_flat + e0 * S), reinterpret_cast<const uint32_t*>(nf), cnt * S, lane);
-  } else if (stepped) {  // rare: an env of the group had its actions rejected and keeps its old outputs
-    if (p.rewards) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(rew + lane * A * rew_elem);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.rewards) + e * A * rew_elem);
-      for (int i = 0; i < A * rew_elem / 4; ++i) dst[i] = src[i];
-    }
-    if (p.next_flat)
-      for (int i = 0; i < S; ++i) p.next_flat[e * S + i] = nf[lane * S + i];
-  }
+  __syncwarp();  // the staged rows are complete before the reads below
+  if (reward_rows(p)) warp_copy_bytes(reward_rows(p) + e0 * rew_row, rew, cnt * rew_row, lane);
+  if (p.next_flat) warp_copy_words(reinterpret_cast<uint32_t*>(p.next_flat + e0 * S), reinterpret_cast<const uint32_t*>(nf), cnt * S, lane);
   warp_expand_byte_rows(p.non_spatial + e0 * F, reinterpret_cast<const uint32_t*>(blk), cnt * F, lane);
 }
 
@@ -551,7 +590,7 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_tma(const __grid_
   em.init(dyn_smem + (size_t)warp * L.per_warp, &L, lane);
   if (ENCODE && p.enc.sp_floats > 0) em.zero_spatial();
   const int64_t n_groups = (p.N + 31) >> 5;
-  const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
+  const int rew_row = reward_row_bytes(p);
   const int64_t g_stride = (int64_t)gridDim.x * L.warps;
   StepInput in, in_next;
   {
@@ -571,29 +610,15 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_tma(const __grid_
     EnvState s = {};
     StepResult r = {};
     em.acquire_dense();  // the previous group's dense bulk stores have finished reading the staging rows
-    step_one<VARIANT>(p, tb, e, have, in, p.rewards ? em.rew() + lane * A * rew_elem : nullptr,
+    step_one<VARIANT>(p, tb, e, have, in, reward_rows(p) ? em.rew() + lane * rew_row : nullptr,
                       p.next_flat ? em.nf() + lane * p.c.S : nullptr, s, r, stepped, finished);
     finish_one(p, tb, e, lane, s, r, stepped, finished);
-    // an env whose actions were rejected keeps its old outputs: do not publish the stale staging rows
-    const bool all_stepped = __all_sync(kFull, stepped || !have);
     bool dense_any = false;
-    if (p.rewards || p.next_flat) {
-      if (!ENCODE) { fence_proxy_async_smem(); __syncwarp(); }  // with ENCODE the fence before the ns drain covers these rows
-      else __syncwarp();
-      if (all_stepped) {
-        if (ENCODE) { fence_proxy_async_smem(); __syncwarp(); }
-        if (p.rewards)
-          dense_any |= drain(static_cast<uint8_t*>(p.rewards) + e0 * A * rew_elem, em.rew(), (uint32_t)(cnt * A * rew_elem), lane);
-        if (p.next_flat) dense_any |= drain(p.next_flat + e0 * p.c.S, em.nf(), (uint32_t)(cnt * p.c.S * 4), lane);
-      } else if (stepped) {  // rare: publish row by row from the lanes that did step
-        if (p.rewards) {
-          const uint32_t* src = reinterpret_cast<const uint32_t*>(em.rew() + lane * A * rew_elem);
-          uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.rewards) + e * A * rew_elem);
-          for (int i = 0; i < A * rew_elem / 4; ++i) dst[i] = src[i];
-        }
-        if (p.next_flat)
-          for (int i = 0; i < p.c.S; ++i) p.next_flat[e * p.c.S + i] = em.nf()[lane * p.c.S + i];
-      }
+    if (reward_rows(p) || p.next_flat) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (reward_rows(p)) dense_any |= drain(reward_rows(p) + e0 * rew_row, em.rew(), (uint32_t)(cnt * rew_row), lane);
+      if (p.next_flat) dense_any |= drain(p.next_flat + e0 * p.c.S, em.nf(), (uint32_t)(cnt * p.c.S * 4), lane);
       if (!ENCODE && dense_any) {
         if (lane == 0) bulk_commit();
         em.committed_dense();
@@ -734,7 +759,7 @@ __global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_step_ws(const __grid_co
   __syncthreads();
   const int64_t n_groups = (p.N + 31) >> 5;
   const int64_t g_stride = (int64_t)gridDim.x * CW;
-  const int rew_elem = p.rewards_dtype == SUS_F64 ? 8 : 4;
+  const int rew_row = reward_row_bytes(p);
   if (warp < CW) {
     // ------------------------------------------------------------------ compute warp
     int64_t g = (int64_t)blockIdx.x * CW + warp;
@@ -761,7 +786,7 @@ __global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_step_ws(const __grid_co
       StepResult r = {};
       uint8_t* rew = slot + L.rew_off;
       float* nf = reinterpret_cast<float*>(slot + L.nf_off);
-      step_one<VARIANT>(p, tb, e, have, in, p.rewards ? rew + lane * A * rew_elem : nullptr,
+      step_one<VARIANT>(p, tb, e, have, in, reward_rows(p) ? rew + lane * rew_row : nullptr,
                         p.next_flat ? nf + lane * c.S : nullptr, s, r, stepped, finished);
       finish_one(p, tb, e, lane, s, r, stepped, finished);
       const ObsState o = obs_of(s);
@@ -772,21 +797,10 @@ __global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_step_ws(const __grid_co
           for (int k = 0; k < A; ++k) persp_ns_row(c, o, k, ns + (k * 32 + lane) * F);
       }
       write_plane_record(c, o, have, reinterpret_cast<uint16_t*>(slot + L.po_off) + lane * 16);
-      const bool all_stepped = __all_sync(kFull, stepped || !have);
       fence_proxy_async_smem();
       __syncwarp();
-      if (all_stepped) {
-        if (p.rewards) drain(static_cast<uint8_t*>(p.rewards) + e0 * A * rew_elem, rew, (uint32_t)(cnt * A * rew_elem), lane);
-        if (p.next_flat) drain(p.next_flat + e0 * c.S, nf, (uint32_t)(cnt * c.S * 4), lane);
-      } else if (stepped) {  // rare: an env of the group had its actions rejected; publish row by row
-        if (p.rewards) {
-          const uint32_t* src = reinterpret_cast<const uint32_t*>(rew + lane * A * rew_elem);
-          uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.rewards) + e * A * rew_elem);
-          for (int i = 0; i < A * rew_elem / 4; ++i) dst[i] = src[i];
-        }
-        if (p.next_flat)
-          for (int i = 0; i < c.S; ++i) p.next_flat[e * c.S + i] = nf[lane * c.S + i];
-      }
+      if (reward_rows(p)) drain(reward_rows(p) + e0 * rew_row, rew, (uint32_t)(cnt * rew_row), lane);
+      if (p.next_flat) drain(p.next_flat + e0 * c.S, nf, (uint32_t)(cnt * c.S * 4), lane);
       for (int k = 0; k < A; ++k)
         drain(p.non_spatial + ((int64_t)k * p.N + e0) * F, ns + k * 32 * F, (uint32_t)(cnt * F * 4), lane);
       __syncwarp();
@@ -1073,6 +1087,29 @@ int flat_size(const SusConfig& c) {
   int S = 3 * A + ((J > 0 || c.variant == SUS_VARIANT_TAGGING) ? 3 * J : 0);  // base.py:211-228
   if (c.variant == SUS_VARIANT_TAGGING) S += 2 * A + 1;                        // tagging.py:42-60
   return S;
+}
+
+int role_actions_host(const SusConfig& c, int is_imposter) {
+  const int A = c.n_imposters + c.n_crew;
+  if (c.variant == SUS_VARIANT_TRAINING_GROUND) return is_imposter ? 6 : 5;
+  const int base = is_imposter ? 7 : 6;
+  return c.variant == SUS_VARIANT_TAGGING ? base + A - 1 : base;
+}
+
+// record geometry of the compact host protocol (SusCompactLayout in the header)
+void compact_layout(const SusConfig& c, SusCompactLayout& L) {
+  const int A = c.n_imposters + c.n_crew;
+  const int n_max = role_actions_host(c, 1);  // the imposter list is the longer one
+  int ab = 1;
+  while ((1 << ab) < n_max) ++ab;
+  L.action_bits = ab;
+  L.action_bytes = (A * ab + 7) / 8;
+  L.n_codes = (int)n_live_codes(c.variant) + 1;
+  int rb = 1;
+  while ((1 << rb) - 1 < L.n_codes) ++rb;  // the all-ones code is reserved for "actions rejected"
+  L.reward_bits = rb;
+  L.result_bytes = (A * rb + 2 + 7) / 8;
+  L.invalid_code = (1 << rb) - 1;
 }
 
 int validate_config(const SusConfig& c) {
@@ -1407,10 +1444,28 @@ int sus_flat_state_size(const SusConfig* cfg) {
 int sus_n_role_actions(const SusConfig* cfg, int is_imposter) {
   if (!cfg) return fail(SUS_ERR_INVALID_ARGUMENT, "cfg is NULL");
   if (int rc = validate_config(*cfg)) return rc;
-  const int A = cfg->n_imposters + cfg->n_crew;
-  if (cfg->variant == SUS_VARIANT_TRAINING_GROUND) return is_imposter ? 6 : 5;
-  const int base = is_imposter ? 7 : 6;
-  return cfg->variant == SUS_VARIANT_TAGGING ? base + A - 1 : base;
+  return role_actions_host(*cfg, is_imposter);
+}
+
+int sus_compact_layout(const SusConfig* cfg, SusCompactLayout* out) {
+  if (!cfg || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (int rc = validate_config(*cfg)) return rc;
+  compact_layout(*cfg, *out);
+  return SUS_OK;
+}
+
+int sus_reward_lut(const SusConfig* cfg, double* out) {
+  if (!cfg || !out) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (int rc = validate_config(*cfg)) return rc;
+  SusCompactLayout L;
+  compact_layout(*cfg, L);
+  DevConfig d;
+  make_dev_config(*cfg, d);
+  const int stride = L.invalid_code + 1;
+  for (int i = 0; i < d.A; ++i)
+    for (int code = 0; code < stride; ++code)
+      out[i * stride + code] = code < L.n_codes ? reward_of_code(d, i, (uint32_t)code) : std::nan("");
+  return SUS_OK;
 }
 
 int sus_encode_shape(const SusConfig* cfg, const SusEncodeSpec* spec, SusEncodeShape* out) {
@@ -1487,8 +1542,11 @@ int sus_env_step(sus_env_t e, const SusStepIO* io, void* stream) {
 }
 
 static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
-  if (io->actions && io->actions_dtype != SUS_U8 && io->actions_dtype != SUS_I32 && io->actions_dtype != SUS_I64)
-    return fail(SUS_ERR_INVALID_ARGUMENT, "actions_dtype must be SUS_U8, SUS_I32 or SUS_I64");
+  if (io->actions && io->actions_dtype != SUS_U8 && io->actions_dtype != SUS_I32 && io->actions_dtype != SUS_I64 &&
+      io->actions_dtype != SUS_PACKED)
+    return fail(SUS_ERR_INVALID_ARGUMENT, "actions_dtype must be SUS_U8, SUS_I32, SUS_I64 or SUS_PACKED");
+  if (io->packed_out && (io->rewards || io->done || io->truncated))
+    return fail(SUS_ERR_INVALID_ARGUMENT, "packed_out replaces rewards / done / truncated: pass those as NULL");
   if (io->rewards && io->rewards_dtype != SUS_F32 && io->rewards_dtype != SUS_F64)
     return fail(SUS_ERR_INVALID_ARGUMENT, "rewards_dtype must be SUS_F32 or SUS_F64");
   DeviceGuard g(e->device);
@@ -1507,6 +1565,12 @@ static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
   p.stats = e->stats; p.err = e->err; p.tick = e->step_tick++; p.N = e->N;
   p.tick_dev = e->dev_ticks ? e->dev_ticks + TICK_STEP : nullptr; p.tick_ctr = tick_counter(e, TICK_STEP);
   p.ret = e->ret; p.ret_sums = e->ret ? e->ret + (size_t)e->N * p.c.A : nullptr; p.gamma = e->gamma;
+  {
+    SusCompactLayout cl;
+    compact_layout(e->cfg, cl);
+    p.packed_out = io->packed_out;
+    p.action_bits = cl.action_bits; p.action_bytes = cl.action_bytes; p.reward_bits = cl.reward_bits; p.result_bytes = cl.result_bytes;
+  }
   e->inj_step = e->inj_reset = e->inj_act = nullptr;
   if (e->N == 0) return SUS_OK;
   cudaStream_t st = (cudaStream_t)stream;

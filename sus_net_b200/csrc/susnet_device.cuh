@@ -230,6 +230,7 @@ __device__ __forceinline__ uint32_t n_role_actions(const DevConfig& c, uint32_t 
 struct StepResult {
   uint32_t kill_m, fix_m, sab_m;  // last event ASSIGNED to each agent in this step (base.py:514-515,523,532)
   double team_reward;
+  uint32_t team_code;  // win (0 none, 1 crew, 2 imposters) + 3 * vote (0 none, 1 crew member ejected, 2 imposter ejected)
   double ret_imp, ret_crew;  // mean return of the imposters / the crew if the episode ended at this step (else 0)
   bool done, trunc;
 };
@@ -248,6 +249,7 @@ __device__ __forceinline__ void step_env(const DevConfig& c, const GridTables& t
   const int A = TA ? TA : c.A, J = TA ? TJ : c.J;
   out.kill_m = out.fix_m = out.sab_m = 0;
   out.team_reward = 0.0;
+  out.team_code = 0;
 
   // action order: identity or Fisher-Yates (base.py:372-374, R4); one nibble per slot
   uint32_t order = 0x76543210u;
@@ -328,6 +330,7 @@ __device__ __forceinline__ void step_env(const DevConfig& c, const GridTables& t
         s.alive &= ~(1u << best);
         const bool was_imp = (s.imp >> best) & 1u;
         out.team_reward += c.r_vote * (was_imp ? -1.0 : 1.0);  // tagging.py:196
+        out.team_code = was_imp ? 6u : 3u;
         s.misc += was_imp ? (1u << 8) : (1u << 16);            // IMP_VOTED_OUT / CREW_VOTED_OUT
       }
       s.tagcnt = 0; s.used = 0; s.timer = 0;  // tagging.py:237-240
@@ -340,11 +343,11 @@ __device__ __forceinline__ void step_env(const DevConfig& c, const GridTables& t
   bool done = false;
   double win = 0.0;
   if (VARIANT == SUS_VARIANT_TRAINING_GROUND) {  // pred_prey.py:78-99
-    if (J != 0 && n_done == J) { done = true; win = c.r_end; s.misc |= 1u << 24; }
-    else if (alive_crew == 0) { done = true; win = -1.0 * c.r_end; s.misc |= 1u << 25; }
+    if (J != 0 && n_done == J) { done = true; win = c.r_end; s.misc |= 1u << 24; out.team_code += 1u; }
+    else if (alive_crew == 0) { done = true; win = -1.0 * c.r_end; s.misc |= 1u << 25; out.team_code += 2u; }
   } else {  // base.py:409-460: crew win is tested first; true at once when J == 0
-    if (alive_imp == 0 || n_done == J) { done = true; win = c.r_end; s.misc |= 1u << 24; }
-    else if (alive_crew <= alive_imp) { done = true; win = -1.0 * c.r_end; s.misc |= 1u << 25; }
+    if (alive_imp == 0 || n_done == J) { done = true; win = c.r_end; s.misc |= 1u << 24; out.team_code += 1u; }
+    else if (alive_crew <= alive_imp) { done = true; win = -1.0 * c.r_end; s.misc |= 1u << 25; out.team_code += 2u; }
   }
   out.team_reward += win;
   out.done = done;
@@ -365,6 +368,40 @@ __device__ __forceinline__ double agent_reward(const DevConfig& c, const EnvStat
   if (i < c.nI) v *= -1.0;             // by INDEX, not by role (base.py:559)
   if (!(s.alive & bit)) v = c.r_dead;  // base.py:562
   if (VARIANT != SUS_VARIANT_TAGGING && v == 0.0) v = c.r_tsr;
+  return v;
+}
+
+// ---- compact host protocol (include/susnet_b200.h, SusCompactLayout): the same reward as a small code.
+// code = dead ? n_live : event + 4 * team_code; n_live = 12 (no vote phase) or 36 (tagging).
+__host__ __device__ __forceinline__ uint32_t n_live_codes(int variant) { return variant == SUS_VARIANT_TAGGING ? 36u : 12u; }
+
+__device__ __forceinline__ uint32_t agent_reward_code(const DevConfig& c, const EnvState& s, const StepResult& r, int i) {
+  const uint32_t bit = 1u << i;
+  if (!(s.alive & bit)) return n_live_codes(c.variant);
+  const uint32_t ev = (r.kill_m & bit) ? 1u : (r.fix_m & bit) ? 2u : (r.sab_m & bit) ? 3u : 0u;
+  return ev + 4u * r.team_code;
+}
+
+// The float64 reward a code stands for, by the SAME operation sequence as step_env() + agent_reward() (so the host's
+// decode table is bit-exact for arbitrary reward constants; multiplications by +-1 are exact, so FMA contraction of
+// `team += r_vote * s` cannot change a bit).
+inline double reward_of_code(const DevConfig& c, int i, uint32_t code) {
+  const bool tagging = c.variant == SUS_VARIANT_TAGGING;
+  const uint32_t n_live = n_live_codes(c.variant);
+  double v;
+  if (code == n_live) {
+    v = c.r_dead;
+  } else {
+    const uint32_t ev = code & 3u, team = code >> 2, win = team % 3u, vote = team / 3u;
+    v = tagging ? 1.0 * c.r_tsr : 0.0;
+    if (ev == 1u) v = c.r_kill; else if (ev == 2u) v = c.r_fix; else if (ev == 3u) v = -1.0 * c.r_sab;
+    double t = 0.0;
+    if (vote) t += c.r_vote * (vote == 2u ? -1.0 : 1.0);
+    t += win == 1u ? c.r_end : (win == 2u ? -1.0 * c.r_end : 0.0);
+    v += t;
+    if (i < c.nI) v *= -1.0;
+  }
+  if (!tagging && v == 0.0) v = c.r_tsr;
   return v;
 }
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 // Drain `bytes` of shared memory to global memory.  Lane 0 issues a TMA bulk store when source, destination and
 // size are 16-byte multiples (the caller commits/waits); otherwise (ragged tail, odd caller pointers) the warp
-// copies 4-byte words itself.  Must be called by all 32 lanes after fence_proxy_async_smem() + __syncwarp().
+// copies 4-byte words (single bytes where the destination or the size is not a multiple of 4) itself.  Must be called by all 32 lanes after fence_proxy_async_smem() + __syncwarp().
 __device__ __forceinline__ bool drain(void* gdst, const void* ssrc, uint32_t bytes, int lane) {
   if (bytes == 0) return false;
   const bool bulk = (((uint32_t)reinterpret_cast<uintptr_t>(gdst) | bytes) & 15u) == 0;
@@ -48,9 +48,15 @@ __device__ __forceinline__ bool drain(void* gdst, const void* ssrc, uint32_t byt
     if (lane == 0) bulk_store(gdst, ssrc, bytes);
     return true;
   }
-  const uint32_t* s = static_cast<const uint32_t*>(ssrc);
-  uint32_t* g = static_cast<uint32_t*>(gdst);
-  for (uint32_t i = lane; i < (bytes >> 2); i += 32) g[i] = s[i];
+  if (((uint32_t)reinterpret_cast<uintptr_t>(gdst) & 3u) == 0) {
+    const uint32_t* s = static_cast<const uint32_t*>(ssrc);
+    uint32_t* g = static_cast<uint32_t*>(gdst);
+    for (uint32_t i = lane; i < (bytes >> 2); i += 32) g[i] = s[i];
+    for (uint32_t i = (bytes & ~3u) + lane; i < bytes; i += 32)  // byte tail (packed result records of a ragged batch)
+      static_cast<uint8_t*>(gdst)[i] = static_cast<const uint8_t*>(ssrc)[i];
+  } else {
+    for (uint32_t i = lane; i < bytes; i += 32) static_cast<uint8_t*>(gdst)[i] = static_cast<const uint8_t*>(ssrc)[i];
+  }
   return false;
 }
 

@@ -424,7 +424,17 @@ class BatchedFourRoomEnv:
         return self._actions[0].cpu().numpy().astype(int)
 
     # ------------------------------------------------------------------ step (base.py:332-407)
-    def step(self, agent_actions=None, featurizer=None, check=None, out=None):
+    @property
+    def compact(self):
+        """The compact host protocol of this env (`sus_net_b200.compact.CompactProtocol`: record geometry, packers and
+        the bit-exact float64 decode table)."""
+        if getattr(self, "_compact", None) is None:
+            from .compact import CompactProtocol
+
+            self._compact = CompactProtocol(self)
+        return self._compact
+
+    def step(self, agent_actions=None, featurizer=None, check=None, out=None, packed_actions=False, packed_out=None):
         """One env step for every env.
 
         agent_actions: (N, A) (batched) or (A,) (reference mode) role-list indices; None in batched mode means the
@@ -434,7 +444,11 @@ class BatchedFourRoomEnv:
         check: validate action indices on the device and raise IndexError like the reference (synchronises);
         defaults to True in reference mode, False in batched mode.
         out: batched mode only -- `(rewards (N,A) f32|f64, dones (N,) bool, truncated (N,) bool)` device tensors to
-        write instead of the env's own output buffers (double-buffering by `HostStepper`)."""
+        write instead of the env's own output buffers (double-buffering by `HostStepper`).
+        packed_actions / packed_out: batched mode, the compact host protocol (`env.compact`): `agent_actions` is an
+        (N, action_bytes) uint8 device tensor of bit-packed role-list indices; `packed_out` an (N, result_bytes) uint8
+        device tensor that receives reward codes + done / truncated bits INSTEAD of rewards / dones / truncated (the
+        step then returns `(next_states, packed_out, None, None, {})`)."""
         if not self._was_reset:
             raise AssertionError("reset() must be called before step()")
         N, A = self.num_envs, self.n_agents
@@ -459,21 +473,34 @@ class BatchedFourRoomEnv:
                     if not 0 <= int(a) < n_role:
                         raise IndexError("list index out of range")
                 agent_actions = np.asarray(agent_actions).reshape(1, A)
-            if isinstance(agent_actions, torch.Tensor) and agent_actions.device == self.device and \
+            if packed_actions:
+                assert self.batched and isinstance(agent_actions, torch.Tensor) and agent_actions.dtype == torch.uint8 \
+                    and agent_actions.device == self.device and agent_actions.is_contiguous() \
+                    and tuple(agent_actions.shape) == (N, self.compact.action_bytes), \
+                    f"packed actions must be a contiguous ({N}, {self.compact.action_bytes}) uint8 tensor on {self.device}"
+                keep = agent_actions
+            elif isinstance(agent_actions, torch.Tensor) and agent_actions.device == self.device and \
                     agent_actions.dtype in (torch.uint8, torch.int32, torch.int64) and agent_actions.is_contiguous():
                 keep = agent_actions
             else:
                 keep = torch.as_tensor(np.asarray(agent_actions) if not isinstance(agent_actions, torch.Tensor)
                                        else agent_actions).to(device=self.device, dtype=torch.int32).contiguous()
-            assert tuple(keep.shape) == (N, A), f"Expected actions of shape {(N, A)}, got {tuple(keep.shape)}"
+            if not packed_actions:
+                assert tuple(keep.shape) == (N, A), f"Expected actions of shape {(N, A)}, got {tuple(keep.shape)}"
             io.actions = keep.data_ptr()
-            io.actions_dtype = _TORCH_TO_SUS[keep.dtype]
+            io.actions_dtype = L.PACKED if packed_actions else _TORCH_TO_SUS[keep.dtype]
             self._applied_actions = keep
-        rewards, done, trunc = (self._rewards, self._done, self._trunc) if out is None else out
-        io.rewards = rewards.data_ptr()
-        io.rewards_dtype = _TORCH_TO_SUS[rewards.dtype]
-        io.done = done.data_ptr()
-        io.truncated = trunc.data_ptr()
+        if packed_out is not None:
+            assert self.batched and packed_out.dtype == torch.uint8 and packed_out.is_contiguous() and \
+                tuple(packed_out.shape) == (N, self.compact.result_bytes) and packed_out.device == self.device
+            io.packed_out = packed_out.data_ptr()
+            rewards, done, trunc = packed_out, None, None
+        else:
+            rewards, done, trunc = (self._rewards, self._done, self._trunc) if out is None else out
+            io.rewards = rewards.data_ptr()
+            io.rewards_dtype = _TORCH_TO_SUS[rewards.dtype]
+            io.done = done.data_ptr()
+            io.truncated = trunc.data_ptr()
         if self.emit_next_states:
             io.next_flat = self._next_flat.data_ptr()
         if self._metrics_buf is not None:

@@ -178,6 +178,17 @@ class SequenceStateFeaturizer:
             self._buffers[n_items] = (sp, ns)
         self._sp_buf, self._ns_buf = self._buffers[n_items]
 
+    def new_buffers(self, n_items):
+        """A fresh (spatial, non_spatial) output pair for `n_items` items (callers that double-buffer, e.g. `HostStepper`)."""
+        sh, dev = self._shape, self.env.device
+        sp = empty_f32((sh.spatial_views, n_items, sh.spatial_floats), dev) if sh.spatial_views else None
+        return sp, empty_f32((sh.non_spatial_views, n_items, sh.non_spatial_floats), dev)
+
+    def bind_buffers(self, sp, ns):
+        """Make `(sp, ns)` (from `new_buffers`) the output pair the next fit / encode / fused step of that size writes."""
+        self._buffers[ns.shape[1]] = (sp, ns)
+        self._sp_buf, self._ns_buf = sp, ns
+
     def fit(self, state_sequence):
         """Featurize a (B, T, S) batch of flattened states (train.py:70-74,346-348) in one kernel launch."""
         if not isinstance(state_sequence, torch.Tensor):

@@ -292,42 +292,6 @@ def test_empty_batch_and_survey_anchors(cuda_lib):
         assert tr == (k == 999)
 
 
-def test_host_stepper_matches_direct_stepping(cuda_lib):
-    """The pipelined host-buffer driver (3 streams, 2 slots) returns what plain stepping returns."""
-    import sus_net_b200 as S
-
-    cfg = CASES["cfg4_base_1v4"]
-    N, T = 3000, 40
-    ref = make_cuda_env(cfg, N, seed=21)
-    env = make_cuda_env(cfg, N, seed=21)
-    ref.reset(); env.reset()
-    acts, want = [], []
-    for t in range(T):  # record a valid action stream and the expected results
-        a = ref.sample_actions().clone()
-        acts.append(a.to(torch.uint8).cpu().pin_memory())
-        _, r, d, tr, _ = ref.step(a)
-        want.append((cpu(r).copy(), cpu(d).copy(), cpu(tr).copy()))
-    feat = S.GlobalFeaturizer(env)
-    torch.cuda.synchronize()
-    stepper = S.HostStepper(env, featurizer=feat)
-    slots = []
-    for t in range(T):
-        slot = stepper.step(acts[t])
-        if t >= 1:  # results of step t-1 are read while step t is in flight
-            pass
-        r, d, tr = stepper.wait(slot)
-        assert np.array_equal(r.numpy(), want[t][0]) and np.array_equal(d.numpy(), want[t][1])
-        assert np.array_equal(tr.numpy(), want[t][2])
-        slots.append(slot)
-    stepper.drain()
-    torch.cuda.synchronize()
-    env.check_actions()
-    assert torch.equal(env.flat_states(torch.int64), ref.flat_states(torch.int64))
-    sp, ns = oracle.encode_global(cfg, cpu(env.flat_states(torch.int64)))
-    views = feat.generate_featurized_states()
-    assert np.array_equal(cpu(views[0][0])[:, 0], sp) and np.array_equal(cpu(views[3][1])[:, 0], ns[3])
-
-
 @pytest.mark.parametrize("k", range(16))
 def test_random_constructor_arguments_match_oracle(cuda_lib, k):
     """Random variants / sizes / NON-INTEGER reward constants (the oracle is pinned against the reference on the same

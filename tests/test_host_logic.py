@@ -43,8 +43,9 @@ def test_struct_layout_matches_header(lib):
     #include <stddef.h>
     #include "susnet_b200.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(SusConfig), sizeof(SusEncodeSpec), sizeof(SusEncodeShape),
-             sizeof(SusStepIO), offsetof(SusConfig, kill_reward), offsetof(SusConfig, num_envs));
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(SusConfig), sizeof(SusEncodeSpec), sizeof(SusEncodeShape),
+             sizeof(SusStepIO), offsetof(SusConfig, kill_reward), offsetof(SusConfig, num_envs),
+             sizeof(SusCompactLayout), offsetof(SusStepIO, packed_out));
       return 0;
     }'''
     import tempfile
@@ -56,7 +57,8 @@ def test_struct_layout_matches_header(lib):
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     want = [C.sizeof(lib.SusConfig), C.sizeof(lib.SusEncodeSpec), C.sizeof(lib.SusEncodeShape), C.sizeof(lib.SusStepIO),
-            lib.SusConfig.kill_reward.offset, lib.SusConfig.num_envs.offset]
+            lib.SusConfig.kill_reward.offset, lib.SusConfig.num_envs.offset, C.sizeof(lib.SusCompactLayout),
+            lib.SusStepIO.packed_out.offset]
     assert [int(x) for x in out] == want
 
 
@@ -65,6 +67,52 @@ def cfg(lib, **kw):
                 shuffle_imposter_index=1, max_time_steps=1000, tag_reset_interval=50, auto_reset=1, num_envs=16)
     base.update(kw)
     return lib.SusConfig(**base)
+
+
+def test_compact_protocol_layout_and_decode_table(lib):
+    """Host calls of the compact host protocol: record geometry per config and the float64 decode table, recomputed here
+    from the reference's reward rules (base.py:511-532,553-563,389-390; tagging.py:162,196)."""
+    L = lib.lib()
+
+    def layout(c):
+        out = lib.SusCompactLayout()
+        assert L.sus_compact_layout(C.byref(c), C.byref(out)) == 0
+        return out
+
+    l4 = layout(cfg(lib))  # cfg4: 7 imposter actions -> 3 bits x 5 = 2 bytes; 13 codes -> 4 bits x 5 + 2 flags = 3 bytes
+    assert (l4.action_bits, l4.action_bytes, l4.reward_bits, l4.result_bytes, l4.n_codes, l4.invalid_code) == (3, 2, 4, 3, 13, 15)
+    l3 = layout(cfg(lib, variant=1, n_crew=2))  # cfg3 tagging 1v2: 9 actions -> 4 bits; 37 codes -> 6 bits x 3 + 2 = 20 bits
+    assert (l3.action_bits, l3.action_bytes, l3.reward_bits, l3.result_bytes, l3.n_codes, l3.invalid_code) == (4, 2, 6, 3, 37, 63)
+    l8 = layout(cfg(lib, variant=1, n_imposters=3, n_crew=5, n_jobs=2))  # 8 agents: 14 actions, 8 x 6 + 2 = 50 bits
+    assert (l8.action_bits, l8.action_bytes, l8.reward_bits, l8.result_bytes) == (4, 4, 6, 7)
+    # decode table of a config with awkward constants
+    c = cfg(lib, variant=1, n_imposters=2, n_crew=3, n_jobs=2, kill_reward=-5.1, complete_job_reward=1.0 / 3.0,
+            sabotage_reward=0.7, time_step_reward=-0.25, game_end_reward=10.3, dead_penalty=-2.2, vote_reward=0.1)
+    lay = layout(c)
+    lut = np.zeros((5, lay.invalid_code + 1))
+    assert L.sus_reward_lut(C.byref(c), lut.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    for i in range(5):
+        for code in range(lay.n_codes):
+            if code == lay.n_codes - 1:
+                want = -2.2
+            else:
+                ev, team = code & 3, code >> 2
+                win, vote = team % 3, team // 3
+                v = [-0.25, -5.1, 1.0 / 3.0, -0.7][ev]
+                t = 0.0
+                if vote:
+                    t += 0.1 * (-1.0 if vote == 2 else 1.0)
+                t += [0.0, 10.3, -10.3][win]
+                v += t
+                want = -v if i < 2 else v
+            assert lut[i, code] == want and np.signbit(lut[i, code]) == np.signbit(want), (i, code)
+        assert np.isnan(lut[i, lay.n_codes:]).all()
+    # base env: zeros become time_step_reward (base.py:389-390), also for a dead agent with dead_penalty == 0
+    c = cfg(lib, time_step_reward=-1.5, dead_penalty=0.0, kill_reward=0.0, complete_job_reward=3.0)
+    lay = layout(c)
+    lut = np.zeros((5, lay.invalid_code + 1))
+    assert L.sus_reward_lut(C.byref(c), lut.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    assert lut[3, 0] == -1.5 and lut[3, 1] == -1.5 and lut[3, lay.n_codes - 1] == -1.5 and lut[0, 2] == -3.0
 
 
 def test_flat_size_and_action_counts(lib):
