@@ -22,8 +22,9 @@ Numbers on the JSON line
             tensors live in L2-compressible memory, so the DRAM bytes per launch (`traffic`, from the ncu capture in
             profiles/) are about a third of the algorithmic bytes and `frac` can exceed 1; `store_stream` gives the
             fraction of the bare SM -> L2 bulk-store stream, which is what binds the kernel then
-  cpu_baseline   the oracle's C port of the reference loop (sample_actions + step + Global encode) timed on this
-            box's host cores (kind "port": the reference is pure Python and cannot travel to the GPU box)
+  cpu_baseline   the UNMODIFIED Python reference's loop (sample_actions + step + GlobalFeaturizer) on every host core of this
+            box, one env per worker process (kind "reference"; its sources travel as the git-ignored baseline/_ref staged by
+            tools/stage_reference.py), with the oracle's C port of the same loop beside it (`port`)
 Environments are independent: ranks own disjoint env-id ranges (weak scaling, no collective on the step path);
 the only collective is the final NCCL all-reduce of the episode statistics.
 """
@@ -56,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the cpu_baseline sample")
+    ap.add_argument("--reference-sample", type=float, default=None, help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -102,7 +104,71 @@ class OracleLoop:
         return self.n_envs * n_steps / dt, dt
 
 
-def cpu_baseline(target_seconds):
+# ---- the UNMODIFIED reference (pure Python; /root/reference here, the staged baseline/_ref on the GPU box) on all host cores
+_REF = {}
+
+
+def _ref_worker_init(seed_base, counter):
+    """One reference env + GlobalFeaturizer per worker process (one env = one 9x9 game, like the reference runs it)."""
+    import numpy as np
+    import torch
+
+    from oracle import ref_harness as H
+
+    env_mod, feat_mod = H.import_reference()
+    torch.set_num_threads(1)
+    with counter.get_lock():
+        ident = counter.value
+        counter.value += 1
+    np.random.seed(seed_base + ident)
+    env = env_mod.FourRoomEnv(n_imposters=1, n_crew=4, n_jobs=5)  # cfg4, the reference's defaults
+    feat = feat_mod.GlobalFeaturizer(env)
+    state, _ = env.reset()
+    _REF.update(env=env, feat=feat, state=state, torch=torch, seq=np.zeros((1, env.flattened_state_size)))
+
+
+def _ref_worker_run(m):
+    """m env-steps of the reference loop of SURVEY.md 8(d): a = env.sample_actions(); env.step(a); featurizer.fit(seq[None]);
+    generate_featurized_states(); reset on done / truncation."""
+    env, feat, torch, seq = _REF["env"], _REF["feat"], _REF["torch"], _REF["seq"]
+    t0 = time.perf_counter()
+    for _ in range(m):
+        a = env.sample_actions()
+        state, _r, done, trunc, _info = env.step(a)
+        if done or trunc:
+            state, _ = env.reset()
+        seq[0] = env.flatten_state(state)
+        feat.fit(torch.tensor(seq).unsqueeze(0))
+        feat.generate_featurized_states()
+    return time.perf_counter() - t0
+
+
+class ReferencePool:
+    def __init__(self, procs):
+        import multiprocessing as mp
+
+        ctx = mp.get_context("fork")
+        self.procs = procs
+        self.pool = ctx.Pool(procs, initializer=_ref_worker_init, initargs=(1234, ctx.Value("i", 0)))
+
+    def step(self, m):
+        """Every worker advances its env m steps; returns (env-steps done, wall seconds)."""
+        t0 = time.perf_counter()
+        self.pool.map(_ref_worker_run, [m] * self.procs, chunksize=1)
+        return self.procs * m, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_available():
+    from oracle import ref_harness as H
+
+    return H.reference_available()
+
+
+def port_baseline(target_seconds):
     threads = os.cpu_count() or 1
     n_envs = 65536
     loop = OracleLoop(n_envs, threads)
@@ -115,32 +181,99 @@ def cpu_baseline(target_seconds):
     }
 
 
+def cpu_baseline(target_seconds):
+    """The reference's own CPU implementation of the path timed on this box's host cores: the unmodified Python reference
+    (one env per worker process, every core) when its sources are staged, with the oracle's C port of the same loop
+    beside it; the port alone otherwise."""
+    port = port_baseline(min(target_seconds, 6.0))
+    if not reference_available():
+        port["note"] = "reference sources not staged (tools/stage_reference.py): C port only"
+        return port
+    # in a fresh interpreter: this process holds a CUDA context, which must not be forked into the worker processes
+    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--reference-sample", str(target_seconds)],
+                         capture_output=True, text=True, timeout=600)
+    try:
+        ref = json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception:  # noqa: BLE001
+        port["note"] = "timing the staged reference failed: " + (res.stderr.strip().splitlines() or ["no output"])[-1][:200]
+        return port
+    ref["port"] = port
+    return ref
+
+
+def reference_sample(target_seconds):
+    """`bench.py --reference-sample S`: ~S seconds of the unmodified reference loop on every host core -> one JSON line."""
+    procs = os.cpu_count() or 1
+    pool = ReferencePool(procs)
+    try:
+        pool.step(20)            # imports, first-call costs
+        m = 200
+        n, dt = pool.step(m)     # calibration, then grow the sample until it fills the target time
+        for _ in range(4):
+            if dt >= 0.7 * target_seconds:
+                break
+            m = max(m + 1, int(m * target_seconds / max(dt, 1e-3)))
+            n, dt = pool.step(m)
+    finally:
+        pool.close()
+    print(json.dumps({
+        "value": n / dt, "unit": UNIT, "cores": procs, "kind": "reference",
+        "sample": f"{procs} worker processes x {m} env-steps of the unmodified reference loop (FourRoomEnv(1, 4, 5).sample_actions "
+                  f"+ step + GlobalFeaturizer.fit + generate_featurized_states, one env per process, {dt:.1f} s)",
+        "per_core": n / dt / procs}))
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores.  The reference is
-    pure Python (it cannot be compiled into oracle/_ref and /root/reference does not exist on the GPU box), so
-    this times the oracle's C port of the same loop with every host thread."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, all of them.  With the
+    reference's sources present (/root/reference, or baseline/_ref staged by tools/stage_reference.py) this is the UNMODIFIED
+    Python reference, one env per worker process; each bench step is a bounded sample (every worker advances its env m
+    steps).  Without them: the oracle's C port of the same loop."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_envs = 65536
-    loop = OracleLoop(n_envs, threads)
-    rate, _ = loop.rate(3)
-    # each step a bounded sample; keep the whole run within a couple of minutes
-    budget = 60.0
     total_steps = args.steps + args.warmup
-    if n_envs * total_steps / rate > budget:
-        n_envs = max(1024, int(rate * budget / total_steps))
+    budget = 75.0  # seconds for the whole --steps K --warmup W run
+    if reference_available():
+        pool = ReferencePool(threads)
+        try:
+            pool.step(20)  # imports, first-call costs
+            pool.step(200)
+            n, dt = pool.step(600)
+            per_worker = n / dt / threads
+            m = max(20, int(per_worker * budget / total_steps))
+            for _ in range(args.warmup):
+                pool.step(m)
+            t0 = time.perf_counter()
+            done = 0
+            for _ in range(args.steps):
+                done += pool.step(m)[0]
+            dt = time.perf_counter() - t0
+        finally:
+            pool.close()
+        value = done / dt
+        kind = "reference"
+        envs_per_step = threads * m
+        sample = (f"{threads} worker processes (one unmodified reference env each) x {m} env-steps per bench step: "
+                  "sample_actions + step + GlobalFeaturizer.fit + generate_featurized_states")
+    else:
+        n_envs = 65536
         loop = OracleLoop(n_envs, threads)
-    loop.rate(args.warmup)
-    value, dt = loop.rate(args.steps)
-    sample = f"{n_envs} envs per step on {threads} host threads (oracle C port of the reference loop)"
+        rate, _ = loop.rate(3)
+        if n_envs * total_steps / rate > budget:
+            n_envs = max(1024, int(rate * budget / total_steps))
+            loop = OracleLoop(n_envs, threads)
+        loop.rate(args.warmup)
+        value, dt = loop.rate(args.steps)
+        kind = "port"
+        envs_per_step = n_envs
+        sample = f"{n_envs} envs per step on {threads} host threads (oracle C port of the reference loop; reference sources not staged)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": n_envs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "env_steps_per_bench_step": envs_per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -483,7 +616,9 @@ def run_b200_arm(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.reference_sample is not None:
+        reference_sample(args.reference_sample)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_b200_arm(args)

@@ -275,6 +275,11 @@ int sus_env_set_ticks(sus_env_t env, uint64_t step_tick, uint64_t reset_epoch, u
 /* Raw structure-of-arrays state (device pointers, bytes per env) for state_dict()/load_state_dict(). */
 int sus_env_state_arrays(sus_env_t env, void **ptrs /*host [4]*/, int32_t *bytes_per_env /*host [4]*/);
 
+/* Device pointers of the finished-episode accumulators (int64[SUS_N_STATS]), the pending invalid-action counter (uint32)
+ * and -- once sus_env_track_returns was called, else NULL / 0 -- the [A][N] running returns followed by the two return sums
+ * (float64), with their sizes in bytes: what a checkpoint has to carry besides sus_env_state_arrays and the ticks. */
+int sus_env_aux_arrays(sus_env_t env, void **ptrs /*host [3]*/, int64_t *bytes /*host [3]*/);
+
 /* Parity mode: raw 32-bit words that replace the Philox output of the NEXT launch that draws from the
  * stream (step_words [N][2A-1], reset_words [N][n_imp+A+J], act_words [N][A]); NULL leaves a stream alone. */
 int sus_env_debug_inject_words(sus_env_t env, const uint32_t *step_words, const uint32_t *reset_words,
@@ -306,10 +311,44 @@ typedef struct SusReplayPush {
   float *next_states;         /* [M][T][S]  ReplayBuffer.next_states */
   uint8_t *r_dones;           /* [M][1]     ReplayBuffer.dones       */
   int16_t *r_imposters;       /* [M][n_imp] ReplayBuffer.imposters   */
+  const int64_t *idx_dev;     /* optional DEVICE copy of the first slot: used instead of `idx` when not NULL, so that a captured
+                                 CUDA graph can be replayed while the caller advances the index on the device */
 } SusReplayPush;
 
 /* ReplayBuffer.add (replay_memory.py:50-72) for a whole batched step; the caller advances idx/size. */
 int sus_replay_push(const SusReplayPush *args /*host*/, int device, void *stream);
+
+/* ---- row (f2): the acting part of train() (src/train.py:349-381) for all envs in one launch ---------------------
+ * Per agent view i of env e: an ALIVE imposter explores with probability eps -- `np.random.random() <= eps`, uniform over
+ * its role list (train.py:363-366) -- or takes the FIRST argmax of its network's Q-values (train.py:367-370); an alive crew
+ * member likewise with the crew network (train.py:373-381); a dead agent keeps action 0 (train.py:352).  The Q-values come
+ * from the caller's networks (any framework; dense layers are outside this library):
+ *   q_imposter  [N][n_imposter_actions], row e = Q-values of env e's single imposter evaluated on ITS agent view
+ *               (imposter_per_view == 0, needs n_imposters == 1), or [A][N][n_imposter_actions] (imposter_per_view == 1);
+ *               NULL = the imposters act uniformly at random (the reference's RandomEquiprobable model)
+ *   q_crew      [A][N][n_crew_actions], view-major; NULL = the crew acts uniformly at random
+ *   eps         DEVICE pointer to epsilon (so a captured CUDA graph sees the current value), or NULL to use eps_value
+ * Draws: Philox words keyed (seed, global env id, act epoch, purpose 5); slot 2i = agent i's explore word
+ * (explore iff word * 2^-32 <= eps), slot 2i + 1 = its random action (bounded).  Consumes one act epoch like
+ * sus_env_sample_actions.  actions: [N][A] role-list indices, SUS_I32 or SUS_U8. */
+typedef struct SusPolicyIO {
+  const float *q_imposter;
+  const float *q_crew;
+  const float *eps;
+  float eps_value;
+  int32_t imposter_per_view;
+  int32_t actions_dtype;
+  int32_t reserved;
+  void *actions;
+} SusPolicyIO;
+int sus_env_select_actions(sus_env_t env, const SusPolicyIO *io /*host*/, void *stream);
+
+/* T-deep sequences of ENCODED features (train.py:318-322,388-389,440-445 keep them as raw states and re-encode all T
+ * every iteration): seq_out[r][t] = newest[r] if t == T-1 or env (r mod n_envs)'s episode just ended (done | truncated),
+ * else seq_in[r][t+1].  rows = views * n_envs items of R floats per time step (view-major tensors [views][N][T][R]);
+ * `newest` [rows][R] is what the fused step wrote.  seq_in and seq_out must not alias. */
+int sus_seq_roll(const float *seq_in, float *seq_out, const float *newest, const uint8_t *done, const uint8_t *truncated,
+                 int64_t rows, int64_t n_envs, int32_t T, int32_t R, int device, void *stream);
 
 /* L2-compressible device memory for the feature tensors (no reference analogue; the reference's tensors live in host
  * memory).  The planes and flat rows are almost all zeros; in an allocation made with cuMemCreate +

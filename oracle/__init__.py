@@ -257,3 +257,30 @@ def encode_flat(cfg, components, flat):
     out = np.zeros((f.shape[0], F), dtype=np.float32)
     lib().orc_encode_flat(C.byref(c), _p(comps), len(comps), _p(f), f.shape[0], _p(out))
     return out
+
+
+def select_actions(cfg, seed, env_ids, act_epoch, alive, imposter_mask, q_imposter, q_crew, eps, imposter_per_view=False):
+    """numpy restatement of the acting part of train() (train.py:349-381) on the susnet draw spec (rng_spec, purpose 5):
+    alive / imposter_mask (N, A); q_imposter (N, nia) [row e = env e's imposter on its own view] or (A, N, nia) or None;
+    q_crew (A, N, nca) or None; -> (N, A) int32 role-list indices."""
+    from . import rng_spec as R
+
+    alive = np.asarray(alive) != 0
+    imp = np.asarray(imposter_mask) != 0
+    N, A = alive.shape
+    w = R.words(seed, env_ids, act_epoch, R.P_POLICY, 2 * A)
+    nia, nca = n_role_actions(cfg, True), n_role_actions(cfg, False)
+    out = np.zeros((N, A), dtype=np.int32)
+    for e in range(N):
+        for i in range(A):
+            if not alive[e, i]:
+                continue  # train.py:352: agent_actions starts as zeros
+            if imp[e, i]:
+                q = None if q_imposter is None else (q_imposter[i, e] if imposter_per_view else q_imposter[e])
+                n = nia
+            else:
+                q = None if q_crew is None else q_crew[i, e]
+                n = nca
+            explore = q is None or float(w[e, 2 * i]) * 2.0 ** -32 <= float(np.float32(eps))
+            out[e, i] = R.bounded(w[e, 2 * i + 1], n) if explore else int(np.argmax(q[:n]))
+    return out

@@ -11,8 +11,9 @@ wrappers on the module replaces them without touching the reference.  The wrappe
 discriminate the call sites by signature and answer with the semantic draw derived
 from the susnet Philox spec (`oracle/rng_spec.py`).
 
-Only usable where `/root/reference` exists (the build container).  The GPU box never
-imports this module: golden fixtures made with it live in `tests/golden/`.
+Usable where the reference's sources exist: `/root/reference` (the build container) or the staged
+copy `baseline/_ref` made by `tools/stage_reference.py` (git-ignored; it travels to the GPU box with the
+working-directory snapshot).  Golden fixtures made with this module live in `tests/golden/`.
 """
 import os
 import sys
@@ -21,8 +22,18 @@ import numpy as np
 
 from . import rng_spec as R
 
-REFERENCE_ROOT = os.environ.get("SUSNET_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "_shims")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SHIMS = os.path.join(_REPO, "tests", "_shims")
+
+
+def _find_reference_root():
+    for cand in (os.environ.get("SUSNET_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "src", "environment")):
+            return cand
+    return os.environ.get("SUSNET_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available():
@@ -40,6 +51,19 @@ def import_reference():
     import src.features as feat_mod  # noqa: E402
 
     return env_mod, feat_mod
+
+
+def import_reference_training():
+    """The reference's callers of the hot path (needs the pygame / matplotlib / ipywidgets / IPython import stubs):
+    returns (src.train, src.replay_memory, src.models.dqn, src.metrics, src.scheduler)."""
+    import_reference()
+    import src.metrics as metrics_mod  # noqa: E402
+    import src.models.dqn as dqn_mod  # noqa: E402
+    import src.replay_memory as replay_mod  # noqa: E402
+    import src.scheduler as sched_mod  # noqa: E402
+    import src.train as train_mod  # noqa: E402
+
+    return train_mod, replay_mod, dqn_mod, metrics_mod, sched_mod
 
 
 class DrawContext:
@@ -270,3 +294,50 @@ class ReferenceBatch:
             if self.auto_reset and (d or t):
                 self._reset_one(i, wr[i])
         return out
+
+
+class DrawDrivenReferenceEnv:
+    """ONE unmodified reference env whose `reset` / `sample_actions` / `step` consume the draws a susnet env with the same
+    (seed, env id) makes, with the same tick contract as the CUDA env's reference mode (no auto-reset: a `reset()` call
+    uses the next RESET epoch).  Everything else is the reference object's own attribute, so the reference's callers
+    (`ReplayBuffer.populate`, `train()`) can drive it unchanged and be compared with the same callers driving the GPU env."""
+
+    def __init__(self, cfg, seed, env_id=0):
+        install()
+        self._cfg = dict(cfg)
+        self._env = make_reference_env(cfg)
+        e = self._env
+        self._cfg.update(n_agents=e.n_agents, n_imposters=e.n_imposters, n_valid=len(e.valid_positions))
+        self._seed, self._ids = seed, np.array([env_id], dtype=np.uint64)
+        self._step_tick = self._reset_epoch = self._act_epoch = 0
+
+    def __getattr__(self, name):
+        return getattr(self._env, name)
+
+    def reset(self, *a, **kw):
+        A, J, nI = self._env.n_agents, self._env.n_jobs, self._cfg["n_imposters"]
+        w = R.words(self._seed, self._ids, self._reset_epoch, R.P_RESET, R.n_reset_slots(nI, A, J))
+        self._reset_epoch += 1
+        _CTX.active, _CTX.cfg, _CTX.reset_words = True, self._cfg, w[0]
+        try:
+            return self._env.reset(*a, **kw)
+        finally:
+            _CTX.active = False
+
+    def sample_actions(self):
+        w = R.words(self._seed, self._ids, self._act_epoch, R.P_ACT, self._env.n_agents)
+        self._act_epoch += 1
+        _CTX.active, _CTX.cfg, _CTX.act_words, _CTX.act_calls = True, self._cfg, w[0], 0
+        try:
+            return self._env.sample_actions()
+        finally:
+            _CTX.active = False
+
+    def step(self, agent_actions):
+        w = R.words(self._seed, self._ids, self._step_tick, R.P_STEP, R.n_step_slots(self._env.n_agents))
+        self._step_tick += 1
+        _CTX.active, _CTX.cfg, _CTX.step_words, _CTX.kill_events = True, self._cfg, w[0], 0
+        try:
+            return self._env.step(agent_actions)
+        finally:
+            _CTX.active = False

@@ -25,10 +25,13 @@ purpose 3  RESET      reset draws of an explicit reset (tick = reset epoch)
                       slots n_imp + A + j         cell of job j (R3, without replacement)
 purpose 2  ACT        slots i             random action of agent i (R6), tick = act epoch
 purpose 4  ACT_FUSED  same, drawn inside a step launch (tick = step tick)
+purpose 5  POLICY     epsilon-greedy acting (train.py:349-381), tick = act epoch
+                      slots 2i            explore word of agent i: explore iff word * 2**-32 <= eps
+                      slots 2i + 1        its random action (bounded by the role list's length)
 """
 import numpy as np
 
-P_STEP, P_AUTORESET, P_ACT, P_RESET, P_ACT_FUSED = 0, 1, 2, 3, 4
+P_STEP, P_AUTORESET, P_ACT, P_RESET, P_ACT_FUSED, P_POLICY = 0, 1, 2, 3, 4, 5
 
 _M0 = np.uint64(0xD2511F53)
 _M1 = np.uint64(0xCD9E8D57)

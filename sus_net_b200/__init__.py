@@ -35,7 +35,16 @@ from .metrics import METRIC_ORDER, STAT_KEYS, EpisodicMetricHandler, SusMetrics 
 from .distributed import reduce_episode_stats, reduce_return_sums, shard_range  # noqa: F401
 from .host_pipeline import HostStepper  # noqa: F401
 from .replay_memory import Batch, ReplayBuffer  # noqa: F401
-from .train import BatchedActor, DQNTeamTrainer, ExponentialSchedule, allreduce_grads, train_batched  # noqa: F401
+from .train import (  # noqa: F401
+    BatchedActor,
+    BatchedTrainingLoop,
+    DQNTeamTrainer,
+    ExponentialSchedule,
+    FeatureSequence,
+    allreduce_grads,
+    train_batched,
+)
+from .compact import CompactProtocol  # noqa: F401
 
 # reference class names, for `from sus_net_b200 import FourRoomEnv` style drop-in use
 FourRoomEnv = BatchedFourRoomEnv

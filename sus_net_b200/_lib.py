@@ -21,6 +21,7 @@ EXPORTED_SYMBOLS = (
     "sus_env_get_ticks", "sus_env_set_ticks", "sus_env_state_arrays", "sus_env_debug_inject_words",
     "sus_launch_count", "sus_replay_push", "sus_env_rollout", "sus_env_track_returns", "sus_env_return_sums",
     "sus_env_device_ticks", "sus_alloc_compressible", "sus_free_compressible", "sus_compact_layout", "sus_reward_lut",
+    "sus_env_select_actions", "sus_seq_roll", "sus_env_aux_arrays",
 )
 
 
@@ -67,8 +68,14 @@ class SusReplayPush(C.Structure):
         ("actions", C.c_void_p), ("actions_dtype", C.c_int32), ("reserved", C.c_int32),
         ("rewards", C.c_void_p), ("done", C.c_void_p), ("truncated", C.c_void_p), ("imposters", C.c_void_p),
         ("states", C.c_void_p), ("r_actions", C.c_void_p), ("r_rewards", C.c_void_p), ("next_states", C.c_void_p),
-        ("r_dones", C.c_void_p), ("r_imposters", C.c_void_p),
+        ("r_dones", C.c_void_p), ("r_imposters", C.c_void_p), ("idx_dev", C.c_void_p),
     ]
+
+
+class SusPolicyIO(C.Structure):
+    _fields_ = [("q_imposter", C.c_void_p), ("q_crew", C.c_void_p), ("eps", C.c_void_p), ("eps_value", C.c_float),
+                ("imposter_per_view", C.c_int32), ("actions_dtype", C.c_int32), ("reserved", C.c_int32),
+                ("actions", C.c_void_p)]
 
 
 class SusNetError(RuntimeError):
@@ -121,9 +128,12 @@ def lib():
         "sus_alloc_compressible": ([C.c_int, u64, C.POINTER(vp), C.POINTER(u64)], C.c_int),
         "sus_free_compressible": ([vp], C.c_int),
         "sus_env_state_arrays": ([vp, C.POINTER(vp), C.POINTER(i32)], C.c_int),
+        "sus_env_aux_arrays": ([vp, C.POINTER(vp), C.POINTER(i64)], C.c_int),
         "sus_env_debug_inject_words": ([vp, vp, vp, vp], C.c_int),
         "sus_launch_count": ([], i64),
         "sus_replay_push": ([C.POINTER(SusReplayPush), C.c_int, vp], C.c_int),
+        "sus_env_select_actions": ([vp, C.POINTER(SusPolicyIO), vp], C.c_int),
+        "sus_seq_roll": ([vp, vp, vp, vp, vp, i64, i64, i32, i32, C.c_int, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)

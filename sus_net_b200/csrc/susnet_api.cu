@@ -1431,6 +1431,20 @@ extern "C" {
 int sus_internal_fail(int code, const char* msg) { return fail(code, msg); }
 void sus_internal_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// susnet_policy.cu: everything k_select_actions needs from a handle; consumes one act epoch (like sus_env_sample_actions)
+int sus_internal_policy_params(sus_env_t e, DevConfig* c, StateArrays* st, uint64_t* tick, uint64_t** tick_dev,
+                               unsigned int** tick_ctr, int64_t* N, int* device) {
+  *c = e->dc; *st = e->st; *N = e->N; *device = e->device;
+  *tick = e->act_epoch++;
+  *tick_dev = e->dev_ticks ? e->dev_ticks + TICK_ACT : nullptr;
+  *tick_ctr = tick_counter(e, TICK_ACT);
+  if (e->N == 0) {
+    DeviceGuard g(e->device);
+    return advance_tick(e, TICK_ACT, 1, nullptr);
+  }
+  return SUS_OK;
+}
+
 int sus_abi_version(void) { return SUS_ABI_VERSION; }
 const char* sus_last_error(void) { return g_last_error.c_str(); }
 int64_t sus_launch_count(void) { return g_launches.load(); }
@@ -1981,6 +1995,14 @@ int sus_env_state_arrays(sus_env_t e, void** ptrs, int32_t* bytes_per_env) {
   if (!e || !ptrs || !bytes_per_env) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   ptrs[0] = e->st.pos; ptrs[1] = e->st.jobpos; ptrs[2] = e->st.aux; ptrs[3] = e->st.met;
   bytes_per_env[0] = 8; bytes_per_env[1] = 8; bytes_per_env[2] = 16; bytes_per_env[3] = 16;
+  return SUS_OK;
+}
+
+int sus_env_aux_arrays(sus_env_t e, void** ptrs, int64_t* bytes) {
+  if (!e || !ptrs || !bytes) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
+  ptrs[0] = e->stats; bytes[0] = SUS_N_STATS * (int64_t)sizeof(unsigned long long);
+  ptrs[1] = e->err; bytes[1] = sizeof(uint32_t);
+  ptrs[2] = e->ret; bytes[2] = e->ret ? (int64_t)(((size_t)e->N * e->dc.A + 2) * sizeof(double)) : 0;
   return SUS_OK;
 }
 

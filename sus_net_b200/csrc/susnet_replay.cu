@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) k_replay_push(const __grid_constant__ Sus
   const int64_t e = gid / TS;
   const int j = (int)(gid - e * TS);
   const int t = j / p.S, k = j - t * p.S;
-  const int64_t slot = (p.idx + e) % p.M;
+  const int64_t slot = ((p.idx_dev ? *p.idx_dev : p.idx) + e) % p.M;
   const bool finished = p.done[e] || p.truncated[e];
   const float cur = p.seq_in[e * TS + j];
   // np.roll(sequence, -1, axis=0); last row <- the new state (replay_memory.py:121-126)

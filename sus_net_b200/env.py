@@ -77,6 +77,28 @@ _WALLS = np.array([[0, 4], [2, 4], [3, 4], [4, 4], [5, 4], [6, 4], [8, 4],
 _TORCH_TO_SUS = {torch.uint8: L.U8, torch.int32: L.I32, torch.int64: L.I64, torch.float32: L.F32, torch.float64: L.F64}
 
 
+class _FieldMap(dict):
+    """`env.state_fields` (base.py:36-43,130-135): keyed by this package's `StateFields`, and ALSO by any other enum with
+    the same member names -- a caller that imported the reference's own `StateFields` after this package was loaded
+    (train.py:353 indexes `env.state_fields[StateFields.ALIVE_AGENTS]`) must find its keys."""
+
+    def __missing__(self, key):
+        name = getattr(key, "name", key)
+        for k, v in self.items():
+            if k.name == name:
+                return v
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or any(k.name == getattr(key, "name", key) for k in self)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
 class _Discrete:
     """The two attributes of gymnasium.spaces.Discrete the reference's callers read."""
 
@@ -187,8 +209,8 @@ class BatchedFourRoomEnv:
         self.n_imposter_actions, self.n_crew_actions = len(IMPOSTER_ACTIONS), len(CREW_ACTIONS)
 
     def _state_fields(self):
-        return {f: i for i, f in enumerate([StateFields.AGENT_POSITIONS, StateFields.ALIVE_AGENTS,
-                                            StateFields.JOB_POSITIONS, StateFields.JOB_STATUS])}
+        return _FieldMap({f: i for i, f in enumerate([StateFields.AGENT_POSITIONS, StateFields.ALIVE_AGENTS,
+                                                      StateFields.JOB_POSITIONS, StateFields.JOB_STATUS])})
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -299,6 +321,7 @@ class BatchedFourRoomEnv:
         """Keep train()'s running returns `G = reward + gamma * G` (train.py:386) for every agent of every env on the
         device; finished episodes add G[imposter_mask].mean() / G[~imposter_mask].mean() to `return_sums()`."""
         L.check(self.lib.sus_env_track_returns(self._h, float(gamma), self._stream()))
+        self._gamma = float(gamma)
 
     def return_sums(self):
         """(2,) float64 device tensor: summed imposter / crew returns of the episodes counted in episode_stats()[0]."""
@@ -568,7 +591,17 @@ class BatchedFourRoomEnv:
             arrays.append(_as_device_bytes(p, self.num_envs * s, self.device).cpu())
         ticks = [C.c_uint64(), C.c_uint64(), C.c_uint64()]
         L.check(self.lib.sus_env_get_ticks(self._h, *[C.byref(t) for t in ticks]))
-        return {"arrays": arrays, "ticks": [t.value for t in ticks], "stats": self.episode_stats().cpu()}
+        # the accumulators a resumed run must continue from: finished-episode statistics, the pending invalid-action
+        # counter, and (if tracked) train()'s running returns G of every agent + the two return sums, with their gamma
+        aux = [None if not p or not n else _as_device_bytes(p, n, self.device).cpu() for p, n in zip(*self._aux_arrays())]
+        return {"arrays": arrays, "ticks": [t.value for t in ticks], "stats": self.episode_stats().cpu(),
+                "aux": aux, "gamma": getattr(self, "_gamma", None)}
+
+    def _aux_arrays(self):
+        ptrs = (C.c_void_p * 3)()
+        sizes = (C.c_int64 * 3)()
+        L.check(self.lib.sus_env_aux_arrays(self._h, ptrs, sizes))
+        return list(ptrs), list(sizes)
 
     def load_state_dict(self, sd):
         ptrs = (C.c_void_p * 4)()
@@ -577,6 +610,17 @@ class BatchedFourRoomEnv:
         for p, s, a in zip(ptrs, sizes, sd["arrays"]):
             _as_device_bytes(p, self.num_envs * s, self.device).copy_(a.to(self.device))
         L.check(self.lib.sus_env_set_ticks(self._h, *[int(t) for t in sd["ticks"]]))
+        aux = sd.get("aux")
+        if aux is not None:
+            if aux[2] is not None:  # returns were tracked: allocate them here too, then restore G, the sums and gamma
+                self.track_returns(sd["gamma"])
+            for (p, n), a in zip(zip(*self._aux_arrays()), aux):
+                if a is not None and p:
+                    assert n == a.numel(), "checkpoint was made for a different batch size"
+                    _as_device_bytes(p, n, self.device).copy_(a.to(self.device))
+        elif "stats" in sd:  # (older checkpoints carry the statistics only)
+            p, n = self._aux_arrays()
+            _as_device_bytes(p[0], n[0], self.device).copy_(sd["stats"].to(self.device).view(torch.uint8))
         self._was_reset = True
         if not self.batched:
             self._sync_host()
@@ -637,9 +681,9 @@ class BatchedFourRoomEnvWithTagging(BatchedFourRoomEnv):
     def _state_fields(self):
         # TUPLE order (tagging.py:221-230).  The reference's own map (tagging.py:15-28) disagrees with its state
         # tuple and breaks every featurizer on this env; documented deviation.
-        return {f: i for i, f in enumerate([StateFields.AGENT_POSITIONS, StateFields.ALIVE_AGENTS,
-                                            StateFields.JOB_POSITIONS, StateFields.JOB_STATUS, StateFields.USED_TAGS,
-                                            StateFields.TAG_COUNTS, StateFields.TAG_RESET_COUNT])}
+        return _FieldMap({f: i for i, f in enumerate([StateFields.AGENT_POSITIONS, StateFields.ALIVE_AGENTS,
+                                                      StateFields.JOB_POSITIONS, StateFields.JOB_STATUS, StateFields.USED_TAGS,
+                                                      StateFields.TAG_COUNTS, StateFields.TAG_RESET_COUNT])})
 
     @property
     def used_tag_actions(self):

@@ -178,6 +178,17 @@ class SequenceStateFeaturizer:
             self._buffers[n_items] = (sp, ns)
         self._sp_buf, self._ns_buf = self._buffers[n_items]
 
+    def clone_for(self, env=None):
+        """A second featurizer of the same kind with its OWN output buffers (e.g. one for acting, one for replay batches)."""
+        import copy
+
+        f = copy.copy(self)
+        f.env = env or self.env
+        f._buffers = {}
+        f._sp_buf = f._ns_buf = None
+        f.B = f.T = None
+        return f
+
     def new_buffers(self, n_items):
         """A fresh (spatial, non_spatial) output pair for `n_items` items (callers that double-buffer, e.g. `HostStepper`)."""
         sh, dev = self._shape, self.env.device

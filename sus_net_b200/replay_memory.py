@@ -41,6 +41,11 @@ class ReplayBuffer:
         self.size = 0
         self._env = None
         self._seq = None
+        # device copies of idx / size: a CUDA-graph replay of collect_step() / sample() cannot take new host integers, so
+        # with `static_buffers=True` (attach) the push kernel reads the slot from `_idx_dev`, sample() scales its draws by
+        # `_size_dev`, and both are advanced on the device
+        self._idx_dev = self._size_dev = None
+        self._static = False
 
     # ---------------------------------------------------------------- reference API
     def add(self, state, action, reward, next_state, done, imposters):
@@ -58,7 +63,11 @@ class ReplayBuffer:
     def sample(self, batch_size, generator=None):
         """replay_memory.py:74-94: uniform with replacement over the filled part."""
         assert self.size > 0, "Replay buffer is empty, can't sample"
-        sample_idx = torch.randint(0, self.size, (batch_size,), device=self.device, generator=generator)
+        if self._static:  # graph-safe: the filled size lives on the device (float64 draws: exact for any ring size)
+            u = torch.rand(batch_size, device=self.device, dtype=torch.float64, generator=generator)
+            sample_idx = (u * self._size_dev).long().clamp_(max=self.max_size - 1)
+        else:
+            sample_idx = torch.randint(0, self.size, (batch_size,), device=self.device, generator=generator)
         return Batch(states=self.states[sample_idx], actions=self.actions[sample_idx], rewards=self.rewards[sample_idx],
                      imposters=self.imposters[sample_idx], next_states=self.next_states[sample_idx],
                      dones=self.dones[sample_idx])
@@ -98,9 +107,10 @@ class ReplayBuffer:
         return step
 
     # ---------------------------------------------------------------- batched collection
-    def attach(self, env):
+    def attach(self, env, static_buffers=False):
         """Bind a batched env (already reset, or reset here) and start every env's sequence from T copies of its
-        current state (replay_memory.py:107-112, train.py:318-322)."""
+        current state (replay_memory.py:107-112, train.py:318-322).  static_buffers: keep every pointer and integer a
+        collect_step() / sample() launch uses fixed or on the device, so the calls can be captured in a CUDA graph."""
         assert env.batched and env.device == self.device
         assert env.flattened_state_size == self.state_size and env.n_agents == self.n_agents
         assert env.num_envs <= self.max_size, "the ring must hold at least one batched step"
@@ -113,6 +123,10 @@ class ReplayBuffer:
         seq = cur[:, None, :].repeat(1, self.trajectory_size, 1)  # a copy even for T == 1 (cur is overwritten every step)
         self._seq = [seq, torch.empty_like(seq)]
         self._cur_flat = cur
+        self._static = bool(static_buffers)
+        if self._static:
+            self._idx_dev = torch.tensor([self.idx], dtype=torch.int64, device=self.device)
+            self._size_dev = torch.tensor([self.size], dtype=torch.int64, device=self.device)
 
     @property
     def state_sequence(self):
@@ -135,10 +149,21 @@ class ReplayBuffer:
             actions_dtype=_TORCH_TO_SUS[applied.dtype], rewards=rewards.data_ptr(), done=dones.data_ptr(),
             truncated=truncated.data_ptr(), imposters=env._imposters_buf.data_ptr(), states=self.states.data_ptr(),
             r_actions=self.actions.data_ptr(), r_rewards=self.rewards.data_ptr(), next_states=self.next_states.data_ptr(),
-            r_dones=self.dones.data_ptr(), r_imposters=self.imposters.data_ptr())
+            r_dones=self.dones.data_ptr(), r_imposters=self.imposters.data_ptr(),
+            idx_dev=self._idx_dev.data_ptr() if self._static else None)
         L.check(env.lib.sus_replay_push(C.byref(p), self.device.index, env._stream()))
-        self._seq.reverse()
+        if self._static:  # same buffers every step (a graph replays fixed pointers): copy the rolled sequence back
+            self._seq[0].copy_(self._seq[1])
+            self._idx_dev.add_(N).remainder_(self.max_size)
+            self._size_dev.add_(N).clamp_(max=self.max_size)
+        else:
+            self._seq.reverse()
         self.idx = (self.idx + N) % self.max_size
         self.size = min(self.size + N, self.max_size)
         return out
+
+    def sync_host_counters(self):
+        """After CUDA-graph replays (which advance only the device copies): read idx / size back (synchronises)."""
+        if self._static:
+            self.idx, self.size = int(self._idx_dev.item()), int(self._size_dev.item())
 

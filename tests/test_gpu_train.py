@@ -57,6 +57,8 @@ def test_train_step_matches_reference_trainer(cuda_lib):
     torch.backends.cuda.matmul.allow_tf32 = False
     trainer = S.DQNTeamTrainer(torch.optim.Adam(imp.parameters(), lr=1e-3), torch.optim.Adam(crew.parameters(), lr=1e-3), gamma=0.9)
     losses = trainer.train_step(batch, feat, imp, imp_t, crew, crew_t)
+    assert isinstance(losses, torch.Tensor) and losses.device == dev  # the losses stay on the device (no host sync)
+    losses = losses.tolist()
     # float32 GEMMs on another device: tolerance 1e-4 relative on the losses, 1e-5 absolute on the updated weights
     assert np.allclose(losses, g["losses"], rtol=1e-4), (losses, g["losses"])
     for name, m in (("imp", imp), ("crew", crew)):
@@ -92,7 +94,56 @@ def test_batched_training_loop_runs_and_acts_within_role_ranges(cuda_lib):
     mask = env.imposter_mask_batch
     assert (acts[~alive] == 0).all() and (acts[mask].max() <= 5) and (acts[~mask].max() <= 4)
     assert torch.equal(acts, S.BatchedActor(env, imp, crew).act_grouped(feat, 0.0, seq[:, -1]))  # sync-free variant
+    assert torch.equal(acts, S.BatchedActor(env, imp, crew).act_kernel(*feat.stacked_views(), 0.0))  # the selection kernel
     k = 2
     want = torch.argmax(imp(views[k][0], views[k][1]), dim=1)
     sel = mask[:, k] & alive[:, k]
     assert torch.equal(acts[sel, k].long(), want[sel])
+
+
+def test_run_experiment_writes_the_references_artefacts(cuda_lib, tmp_path):
+    """Row f4: config.json with the reference's keys (train.py:185-207), checkpoints at the reference's cadence
+    (train.py:310,331-338,453-459) and metrics.json in the reference's schema, loadable by ITS EpisodicMetricHandler
+    (metrics.py:88-95)."""
+    import json
+
+    import sus_net_b200 as S
+    from sus_net_b200.experiment import run_experiment
+
+    cfg = dict(CASES["base_fixed_order_tsr"], max_time_steps=12)
+    N = 1024
+    env = make_cuda_env(cfg, N, seed=5)
+    feat = flat_featurizer(env, ["onehot_pos", "alive_crew", "closest_crew"])
+    F_ = int(feat.featurized_shape[1][0])
+    torch.manual_seed(0)
+    imp, crew = MLPQ([F_ * 2, 32, env.n_imposter_actions]).to(env.device), MLPQ([F_ * 2, 16, env.n_crew_actions]).to(env.device)
+    m = run_experiment(env, 60, imp, crew, feat, sequence_length=2, replay_buffer_size=4 * N, replay_prepopulate_steps=2 * N,
+                       batch_size=128, gamma=0.9, scheduler_time_steps=50, experiment_base_dir=tmp_path, learning_rate=1e-3,
+                       train_step_interval=5, num_checkpoint_saves=4, target_update_interval=20, use_graphs=True, log_interval=20)
+    d = m.experiment_dir
+    files = sorted(p.name for p in d.iterdir())
+    assert files == sorted(["config.json", "metrics.json", "metrics_totals.json"] + [f"{t}_MLPQ_{p}.pt" for t in ("imposter", "crew")
+                                                                                      for p in ("0", "33", "66", "100%")]), files
+    conf = json.loads((d / "config.json").read_text())
+    ref_keys = {"num_steps", "imposter_model_args", "crew_model_args", "imposter_model_type", "crew_model_type", "featurizer_type",
+                "sequence_length", "replay_buffer_size", "replay_prepopulate_steps", "batch_size", "gamma", "scheduler_start_eps",
+                "scheduler_end_eps", "scheduler_time_steps", "train_imposter", "train_crew", "experiment_base_dir",
+                "optimizer_type", "learning_rate", "train_step_interval", "target_update_interval"}
+    assert ref_keys <= set(conf) and conf["num_steps"] == 60 and conf["sequence_length"] == 2
+    ck = torch.load(d / "imposter_MLPQ_100%.pt", weights_only=False)
+    assert set(ck) == {"state_dict", "config"} and all(torch.equal(v.cpu(), imp.state_dict()[k].cpu()) for k, v in ck["state_dict"].items())
+    mj = json.loads((d / "metrics.json").read_text())
+    assert set(mj) == {str(x.value) for x in S.SusMetrics} and all(isinstance(v, list) and len(v) >= 1 for v in mj.values())
+    assert len(mj["imposter_loss"]) == 12 and len(mj["crew_won"]) == 3 and len(mj["avg_imposter_returns"]) == 3
+    tot = json.loads((d / "metrics_totals.json").read_text())
+    assert tot["episodes"] > N and tot["iterations"] == 60 and 0 < tot["averages"]["crew_won"] + tot["averages"]["imposter_won"] <= 1
+    from oracle import ref_harness as H
+
+    if H.reference_available():  # the reference's own handler loads and averages the file
+        H.import_reference()
+        from src.metrics import EpisodicMetricHandler as Ref
+
+        r = Ref()
+        r.load_metrics(d / "metrics.json")
+        avg = r.compute()
+        assert len(avg) == 13 and abs(avg["crew_won"] - np.mean(mj["crew_won"])) < 1e-12

@@ -128,3 +128,97 @@ def test_gradient_allreduce_two_ranks_gloo(S):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_flat_adam_equals_torch_adam_and_gates_empty_subsets(S):
+    """`_FlatAdam` (the device-gated optimizer step of the sync-free trainer) == torch.optim.Adam when the subset is not empty;
+    with a zero sample count weights, moments and the step count stay untouched (the reference `continue`s, train.py:88-92)."""
+    from sus_net_b200.train import _FlatAdam
+
+    torch.manual_seed(0)
+    make = lambda: torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.PReLU(), torch.nn.Linear(5, 3))  # noqa: E731
+    a, b = make(), make()
+    b.load_state_dict(a.state_dict())
+    ref = torch.optim.Adam(a.parameters(), lr=1e-2)
+    fa = _FlatAdam(torch.optim.Adam(b.parameters(), lr=1e-2))
+    for step in range(6):
+        x, y = torch.randn(9, 6), torch.randn(9, 3)
+        ref.zero_grad()
+        torch.nn.functional.mse_loss(a(x), y).backward()  # mean over 9 x 3 elements
+        ref.step()
+        fa.begin_train_step(); fa.begin_view()
+        sq = ((b(x) - y) ** 2).sum()
+        sq.backward()
+        loss = fa.apply(torch.tensor(27.0), sq.detach())
+        assert float(loss) == pytest.approx(float(sq) / 27, rel=1e-6)
+        for p, q in zip(a.parameters(), b.parameters()):
+            assert torch.allclose(p, q, atol=1e-6), step
+        if step == 3:  # an empty subset in between: nothing may move
+            before = [q.detach().clone() for q in b.parameters()]
+            m, v, st = fa.m.clone(), fa.v.clone(), fa.step.clone()
+            fa.begin_train_step(); fa.begin_view()
+            assert float(fa.apply(torch.tensor(0.0), torch.tensor(0.0))) == 0.0
+            assert all(torch.equal(p, q) for p, q in zip(before, b.parameters()))
+            assert torch.equal(m, fa.m) and torch.equal(v, fa.v) and torch.equal(st, fa.step)
+
+
+_FLAT_ADAM_WORKER = r'''
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sus_net_b200.train import _FlatAdam
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+torch.manual_seed(0)
+make = lambda: torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.PReLU(), torch.nn.Linear(3, 2))
+m, single = make(), make()
+single.load_state_dict(m.state_dict())
+X, Y = torch.randn(10, 4), torch.randn(10, 2)
+rows = [slice(0, 7), slice(7, 10)][rank]          # uneven local subsets: 7 and 3 samples
+fa = _FlatAdam(torch.optim.Adam(m.parameters(), lr=1e-2))
+ref = torch.optim.Adam(single.parameters(), lr=1e-2)
+for step in range(4):
+    fa.begin_train_step(); fa.begin_view()
+    sq = ((m(X[rows]) - Y[rows]) ** 2).sum(dim=1).sum()
+    sq.backward()
+    loss = fa.apply(torch.tensor(float(rows.stop - rows.start)), sq.detach())
+    # single process on the whole batch: mean over the 10 samples (every sample weighs the same)
+    ref.zero_grad()
+    full = ((single(X) - Y) ** 2).sum(dim=1).mean()
+    full.backward()
+    ref.step()
+    assert abs(float(loss) - float(full)) < 1e-5
+    for p, q in zip(m.parameters(), single.parameters()):
+        assert torch.allclose(p, q, atol=1e-6), (step, rank)
+# a subset that is empty on EVERY rank: no rank moves
+before = [p.detach().clone() for p in m.parameters()]
+fa.begin_train_step(); fa.begin_view()
+fa.apply(torch.tensor(0.0), torch.tensor(0.0))
+assert all(torch.equal(p, q) for p, q in zip(before, m.parameters()))
+# empty on this rank only: it still takes the other rank's step
+fa.begin_train_step(); fa.begin_view()
+if rank == 0:
+    sq = ((m(X) - Y) ** 2).sum()
+    sq.backward()
+    fa.apply(torch.tensor(10.0), sq.detach())
+else:
+    fa.apply(torch.tensor(0.0), torch.tensor(0.0))
+flat = fa.flat.clone()
+dist.all_reduce(flat)
+assert torch.allclose(flat, 2 * fa.flat, atol=1e-7) and not all(torch.equal(p, q) for p, q in zip(before, m.parameters()))
+dist.destroy_process_group()
+'''
+
+
+def test_flat_adam_two_ranks_gloo_weights_samples_evenly(S):
+    """World size 2 (gloo): gradient SUMS, sample counts and loss sums ride in one all-reduce, so uneven local subsets give
+    exactly the single-process step on the union; a globally empty subset moves nothing on any rank."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = str(33000 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, "-c", _FLAT_ADAM_WORKER, root, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

@@ -106,7 +106,10 @@ def main():
     replay_fixture("base_2v3_j3", T=3, M=64)
     replay_fixture("tagging_2v5_short", T=2, M=50)
     train_step_fixture()
-    if "--replay-only" in sys.argv:
+    acting_fixture("acting.cfg4_global_spatial_T2", dict(CASES["cfg4_base_1v4"], max_time_steps=40), "global", T=2, steps=260)
+    acting_fixture("acting.cfg4alt_flat98_mlp_T1", dict(CASES["cfg4alt_itg_1v4"], shuffle_imposter_index=True), "flat", T=1,
+                   steps=1010)
+    if "--replay-only" in sys.argv or "--acting-only" in sys.argv:
         return
     for name in CASES:
         for injected in (False, True):
@@ -231,5 +234,76 @@ def train_step_fixture():
     print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB, losses {losses}")
 
 
+def acting_fixture(tag, cfg, kind, T, steps):
+    """Row f2: the reference's OWN greedy acting (src/train.py:349-381, unmodified `train()` with epsilon ~ 0 and a trainer
+    without optimizers, so nothing is trained) on its own env, featurizer and randomly initialised networks.  The replay
+    ring it fills holds, per transition, the state sequence the actions were taken from, the imposter ids and the actions:
+    known answers for `BatchedActor` / `sus_env_select_actions` at eps = 0."""
+    import contextlib
+    import io
+    import pathlib
+    import tempfile
+
+    import torch
+
+    train_mod, replay_mod, dqn_mod, metrics_mod, sched_mod = H.import_reference_training()
+    _, feat_mod = H.import_reference()
+
+    class RandomlyDriven(H.DrawDrivenReferenceEnv):
+        """The env advances on RANDOM actions (diverse states, kills, dead agents) while train() records the greedy actions
+        its unmodified acting code chose for each state: the recorded (state, action) pairs are what the fixture pins."""
+
+        def step(self, agent_actions):
+            return super().step(self.sample_actions())
+
+    env = RandomlyDriven(cfg, SEED, env_id=ENV_ID_BASE)
+    e = env._env
+    if kind == "global":
+        feat = feat_mod.GlobalFeaturizer(e)
+        ns = int(feat.featurized_shape[1][0])
+        spatial = dict(input_image_size=9, non_spatial_input_size=ns, n_channels=[e.n_agents + 2, 6, 6], strides=[1, 1],
+                       paddings=[1, 1], kernel_size=[3, 3], dilations=[1, 1], rnn_layers=1, rnn_hidden_dim=24,
+                       rnn_dropout=0.0, mlp_hidden_layer_dims=[16])
+        torch.manual_seed(5)
+        imp = dqn_mod.SpatialDQN(n_actions=e.n_imposter_actions, **spatial)
+        crew = dqn_mod.SpatialDQN(n_actions=e.n_crew_actions, **spatial)
+    else:
+        feat = feat_mod.FlatFeaturizer(e, feat_mod.CompositeFeaturizer([feat_mod.OneHotAgentPositionFeaturizer(e),
+                                                                        feat_mod.AliveCrewFeaturizer(e),
+                                                                        feat_mod.ClosestAliveCrewFeaturizer(e)]))
+        torch.manual_seed(5)
+        imp = dqn_mod.MLP([98 * T, 48, 24, e.n_imposter_actions])
+        crew = dqn_mod.MLP([98 * T, 32, e.n_crew_actions])
+    with torch.no_grad():  # larger weights: the argmax depends on the input instead of on the output biases
+        for m in (imp, crew):
+            for p_ in m.parameters():
+                if p_.dim() > 1:
+                    p_.mul_(4.0)
+    np.random.seed(99)
+    rb = replay_mod.ReplayBuffer(max_size=steps, trajectory_size=T, state_size=e.flattened_state_size,
+                                 n_imposters=e.n_imposters, n_agents=e.n_agents)
+    trainer = train_mod.DQNTeamTrainer(imposter_optimizer=None, crew_optimizer=None, gamma=0.9)
+    with tempfile.TemporaryDirectory() as d, contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        train_mod.train(env=env, metrics=metrics_mod.EpisodicMetricHandler(), num_steps=steps, replay_buffer=rb, featurizer=feat,
+                        imposter_model=imp, crew_model=crew, scheduler=sched_mod.ExponentialSchedule(1e-12, 1e-12, 2),
+                        save_directory_path=pathlib.Path(d), trainer=trainer, train_step_interval=5, batch_size=8, num_saves=2,
+                        target_update_interval=10_000)
+    assert rb.size == steps
+    out = dict(kind=kind, T=T, states=rb.states.numpy(), actions=rb.actions.numpy().astype(np.int8),
+               imposters=rb.imposters.numpy(), cfg_json=np.frombuffer(__import__("json").dumps(cfg).encode(), dtype=np.uint8))
+    out.update({f"imp.{k}": v.detach().numpy() for k, v in imp.state_dict().items()})
+    out.update({f"crew.{k}": v.detach().numpy() for k, v in crew.state_dict().items()})
+    path = os.path.join(OUT, f"{tag}.npz")
+    np.savez_compressed(path, **out)
+    alive = rb.states.numpy()[:, -1, 2 * e.n_agents:3 * e.n_agents] != 0
+    print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB, {steps} greedy steps, {int((~alive).sum())} dead-agent slots, "
+          f"action histogram {np.bincount(out['actions'].reshape(-1).astype(np.int64)).tolist()}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--acting-only" in sys.argv:
+        acting_fixture("acting.cfg4_global_spatial_T2", dict(CASES["cfg4_base_1v4"], max_time_steps=40), "global", T=2, steps=260)
+        acting_fixture("acting.cfg4alt_flat98_mlp_T1", dict(CASES["cfg4alt_itg_1v4"], shuffle_imposter_index=True), "flat", T=1,
+                       steps=1010)
+    else:
+        main()
