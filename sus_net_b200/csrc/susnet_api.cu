@@ -494,6 +494,144 @@ __global__ void __launch_bounds__(kThreads, kFlatMinCtas) k_step_flat(const __gr
   warp_expand_byte_rows(p.non_spatial + e0 * F, reinterpret_cast<const uint32_t*>(blk), cnt * F, lane);
 }
 
+// K1+K2 for FLAT encodes, warp-specialised (the Flat counterpart of k_step_ws): the step is latency-bound, so what pays is
+// many resident compute warps with few instructions each.  Here up to 28 compute warps per persistent CTA only run the step and
+// leave, per group of 32 envs, a ROW RECORD in shared memory -- the K non-zero (offset, value) entries of each env's row, 32 x K x
+// 2 bytes instead of the 32 x F bytes / 128 F bytes the staged / TMA paths hold per warp -- and a few emitter warps turn records
+// into rows: each owns ONE persistently-zero tile of 32 rows x F floats, sets the entries of a group (lane = row), hands the
+// tile to the TMA engine with one cp.async.bulk, and clears the same entries once the engine has read the tile.  The compute
+// warps never touch the F floats of a row, the emitters never compute a step; rewards / the replay row / packed result records
+// are staged and bulk-stored by the compute warps themselves.
+struct FlatWsLayout {
+  int32_t compute_warps, emitter_warps;
+  int32_t K;                              // entries per env in a record (multiple of 8)
+  int32_t tile_bytes, rec_bytes;          // one emitter tile (32 x F floats); one record (32 x K x 2 bytes)
+  int32_t dense_bytes, rew_off, nf_off;   // per compute warp: rewards / packed records + next_flat staging
+  int32_t recs_off, dense_off, bars_off, total_bytes;  // inside dynamic shared memory (tiles first)
+};
+
+constexpr int kFlatWsMaxWarps = 32;
+template <int VARIANT, int TA = 0, int TJ = 0>
+__global__ void __launch_bounds__(kFlatWsMaxWarps * 32, 1) k_step_flat_ws(const __grid_constant__ StepParams p,
+                                                                          const __grid_constant__ FlatWsLayout L) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __shared__ GridTables tb;
+  stage_tables_and_tick(p.c, tb, p.tick, p.tick_dev, p.tick_ctr);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int CW = L.compute_warps, EW = L.emitter_warps, F = p.enc.ns_floats, K = L.K, S = p.c.S;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + L.bars_off);  // full[w*2+s], then empty[w*2+s]
+  {
+    float4* t = reinterpret_cast<float4*>(dyn_smem);
+    for (int i = threadIdx.x; i < (EW * L.tile_bytes) >> 4; i += blockDim.x) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 4 * CW; ++i) mbar_init(&bars[i], 1);
+  }
+  __syncthreads();
+  const int64_t n_groups = (p.N + 31) >> 5;
+  const int64_t g_stride = (int64_t)gridDim.x * CW;
+  const int rew_row = reward_row_bytes(p);
+  if (warp < CW) {
+    // ------------------------------------------------------------------ compute warp
+    uint8_t* dense = dyn_smem + L.dense_off + (size_t)warp * L.dense_bytes;
+    uint8_t* rew = dense + L.rew_off;
+    float* nf = reinterpret_cast<float*>(dense + L.nf_off);
+    const bool dense_out = reward_rows(p) != nullptr || p.next_flat != nullptr;
+    int64_t g = (int64_t)blockIdx.x * CW + warp;
+    for (int it = 0; g < n_groups; ++it, g += g_stride) {
+      const int64_t e0 = g << 5, e = e0 + lane;
+      const bool have = e < p.N;
+      const int cnt = p.N - e0 < 32 ? (int)(p.N - e0) : 32;
+      StepInput in;
+      load_input(p, e, have, in);
+      const int sl = it & 1;
+      uint16_t* rec = reinterpret_cast<uint16_t*>(dyn_smem + L.recs_off + (size_t)(warp * 2 + sl) * L.rec_bytes);
+      if (it >= 2) mbar_wait(&bars[2 * CW + warp * 2 + sl], (uint32_t)(((it >> 1) - 1) & 1));  // the emitter has read this record slot
+      if (it >= 1 && dense_out) {  // my dense stores of the previous group have been read (single staging block)
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+      }
+      bool stepped, finished;
+      EnvState s = {};
+      StepResult r = {};
+      step_one<VARIANT, TA, TJ>(p, tb, e, have, in, reward_rows(p) ? rew + lane * rew_row : nullptr,
+                                p.next_flat ? nf + lane * S : nullptr, s, r, stepped, finished);
+      finish_one(p, tb, e, lane, s, r, stepped, finished);
+      {
+        uint4* mine = reinterpret_cast<uint4*>(rec + lane * K);
+        for (int i = 0; i < (K >> 3); ++i) mine[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (have) flat_row_record(p.c, p.enc, tb, obs_of(s), rec + lane * K, K);
+      }
+      if (dense_out) fence_proxy_async_smem();
+      __syncwarp();
+      if (dense_out) {
+        bool any = false;
+        if (reward_rows(p)) any |= drain(reward_rows(p) + e0 * rew_row, rew, (uint32_t)(cnt * rew_row), lane);
+        if (p.next_flat) any |= drain(p.next_flat + e0 * S, nf, (uint32_t)(cnt * S * 4), lane);
+        if (lane == 0 && any) bulk_commit();
+      }
+      if (lane == 0) mbar_arrive(&bars[warp * 2 + sl]);  // the record is ready for the emitter
+    }
+    if (lane == 0) bulk_wait_all();
+  } else if (warp < CW + EW) {
+    // ------------------------------------------------------------------ emitter warp: serves compute warps em, em + EW, ...
+    const int em = warp - CW;
+    float* tile = reinterpret_cast<float*>(dyn_smem + (size_t)em * L.tile_bytes);
+    constexpr int kMaxK = 16;
+    uint32_t prev[kMaxK];  // float indices this lane set in the tile (0xffffffff = none)
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) prev[j] = 0xffffffffu;
+    bool inflight = false;
+    const int64_t base_g = (int64_t)blockIdx.x * CW;
+    for (int it = 0; base_g + (int64_t)it * g_stride < n_groups; ++it) {
+      const int sl = it & 1;
+      for (int w = em; w < CW; w += EW) {
+        const int64_t g = base_g + w + (int64_t)it * g_stride;
+        if (g >= n_groups) break;
+        mbar_wait(&bars[w * 2 + sl], (uint32_t)((it >> 1) & 1));
+        const uint16_t* rec = reinterpret_cast<const uint16_t*>(dyn_smem + L.recs_off + (size_t)(w * 2 + sl) * L.rec_bytes) + lane * K;
+        uint32_t ent[kMaxK];
+#pragma unroll
+        for (int q = 0; q < kMaxK / 8; ++q) {  // all loads first
+          uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (q * 8 < K) v = reinterpret_cast<const uint4*>(rec)[q];
+          ent[8 * q + 0] = v.x & 0xffffu; ent[8 * q + 1] = v.x >> 16; ent[8 * q + 2] = v.y & 0xffffu; ent[8 * q + 3] = v.y >> 16;
+          ent[8 * q + 4] = v.z & 0xffffu; ent[8 * q + 5] = v.z >> 16; ent[8 * q + 6] = v.w & 0xffffu; ent[8 * q + 7] = v.w >> 16;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2 * CW + w * 2 + sl]);  // the record slot may be refilled
+        if (inflight) {
+          if (lane == 0) bulk_wait_read_all();  // the engine has read my tile
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j)
+          if (prev[j] != 0xffffffffu) tile[prev[j]] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j) {
+          if (ent[j] != kRecordNone) {
+            const uint32_t idx = (uint32_t)(lane * F) + (ent[j] & 0x3ffu);
+            tile[idx] = record_value(ent[j]);
+            prev[j] = idx;
+          } else {
+            prev[j] = 0xffffffffu;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int64_t e0 = g << 5;
+        const int cnt = p.N - e0 < 32 ? (int)(p.N - e0) : 32;
+        if (drain(p.non_spatial + e0 * F, tile, (uint32_t)(cnt * F * 4), lane)) {
+          if (lane == 0) bulk_commit();
+          inflight = true;
+        } else {
+          inflight = false;
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+}
+
 // Random-policy rollout: every env advances `n_steps` steps inside ONE launch with its state in registers
 // (== n_steps calls of step(None): same ticks, same draws, same auto-resets, same episode statistics); only the final
 // state and, optionally, the per-agent reward sums are written.  This is ReplayBuffer.populate's / a random-policy
@@ -1289,6 +1427,62 @@ bool make_flat_stage(const DevConfig& c, const DevEncode& enc, int rew_elem, boo
   return per_cta <= (size_t)max_dyn_smem && per_cta * kFlatMinCtas <= 227u * 1024u;
 }
 
+// Upper bound of the non-zero values of a flat row (the record size of k_step_flat_ws); -1 if a component is float-valued.
+int flat_max_nonzeros(const DevConfig& c, const DevEncode& enc) {
+  const int A = c.A, J = c.J;
+  int k = 0;
+  for (int q = 0; q < enc.n_components; ++q) {
+    switch (enc.components[q]) {
+      case SUS_FC_ONEHOT_POS: k += 2 * A; break;
+      case SUS_FC_COORDS: k += 2 * A; break;
+      case SUS_FC_ALIVE_CREW: k += A - 1; break;
+      case SUS_FC_CLOSEST_CREW: k += 1; break;
+      case SUS_FC_L1_CREW: k += A - 1; break;
+      case SUS_FC_DIST_TO_IMPOSTER: k += 2 * (A - 1); break;
+      case SUS_FC_WALLS: k += 9; break;
+      case SUS_FC_ROOMS: k += 1 + (A - 1 < 4 ? A - 1 : 4); break;
+      case SUS_FC_STATE_ALIVE: k += A; break;
+      case SUS_FC_STATE_JOB_STATUS: k += J; break;
+      case SUS_FC_STATE_USED_TAGS: k += A; break;
+      case SUS_FC_STATE_TAG_COUNTS: k += A; break;
+      default: return -1;  // SUS_FC_SCENT: float-valued
+    }
+  }
+  return k;
+}
+
+// Layout of k_step_flat_ws; false if it does not apply (float-valued component, too many non-zeros per row, rows longer than
+// the 10-bit offsets) or does not fit.  Measured at 1 Mi envs, cfg4-alt Flat-98 (tools/ab_flat.py): see DESIGN.md.
+bool make_flat_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_row_bytes, bool want_nf, int max_dyn_smem,
+                         FlatWsLayout& L) {
+  if (enc.kind != SUS_ENCODE_FLAT || enc.ns_floats >= 1023) return false;
+  const int nz = flat_max_nonzeros(c, enc);
+  if (nz < 0 || nz > 16) return false;
+  FlatWsLayout t = {};
+  t.K = (nz + 7) & ~7;
+  if (t.K == 0) t.K = 8;
+  t.tile_bytes = align128((int64_t)32 * enc.ns_floats * 4);
+  t.rec_bytes = 32 * t.K * 2;
+  t.rew_off = 0;
+  t.nf_off = align128((int64_t)32 * rew_row_bytes);
+  t.dense_bytes = t.nf_off + (want_nf ? align128((int64_t)32 * c.S * 4) : 0);
+  const char* env_e = std::getenv("SUSNET_FLATWS_EMITTERS");
+  const char* env_w = std::getenv("SUSNET_FLATWS_WARPS");
+  t.emitter_warps = env_e && std::atoi(env_e) > 0 ? std::atoi(env_e) : 4;
+  const int budget = max_dyn_smem - 2048 - t.emitter_warps * t.tile_bytes - 512;
+  int cw = budget / (2 * t.rec_bytes + t.dense_bytes);
+  if (cw > kFlatWsMaxWarps - t.emitter_warps) cw = kFlatWsMaxWarps - t.emitter_warps;
+  if (env_w && std::atoi(env_w) > 0 && std::atoi(env_w) < cw) cw = std::atoi(env_w);
+  if (cw < 2 * t.emitter_warps) return false;
+  t.compute_warps = cw;
+  t.recs_off = t.emitter_warps * t.tile_bytes;
+  t.dense_off = t.recs_off + 2 * cw * t.rec_bytes;
+  t.bars_off = t.dense_off + cw * t.dense_bytes;
+  t.total_bytes = t.bars_off + 4 * cw * 8;
+  L = t;
+  return true;
+}
+
 // Warp-specialised layout (susnet_ws.cuh); returns false if it does not apply or does not fit.
 // `fast_sink`: the plane tensor lives in L2-compressible memory (sus_alloc_compressible), where the tile stores drain
 // ~18 % faster.  Measured at 1 Mi envs (tools/ab_flat.py under SUSNET_WS_TILE / SUSNET_WS_WARPS): Global into a fast sink
@@ -1615,6 +1809,34 @@ static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
         break;
     }
     return after_launch("k_step_ws");
+  }
+  FlatWsLayout FW;
+  if (want_ws() && enc && make_flat_ws_layout(p.c, p.enc, io->packed_out ? p.result_bytes : p.c.A * (io->rewards_dtype == SUS_F64 ? 8 : 4),
+                                              io->next_flat != nullptr, di.max_dyn_smem, FW)) {
+    const int64_t groups = (e->N + 31) / 32;
+    const int64_t ctas = (groups + FW.compute_warps - 1) / FW.compute_warps;
+    const unsigned gr = (unsigned)(ctas < di.sms ? ctas : di.sms);
+    const unsigned threads = (unsigned)(FW.compute_warps + FW.emitter_warps) * 32;
+    switch (e->cfg.variant) {
+      case SUS_VARIANT_BASE:
+        if (int rc = allow_big_smem(k_step_flat_ws<SUS_VARIANT_BASE>, FW.total_bytes)) return rc;
+        k_step_flat_ws<SUS_VARIANT_BASE><<<gr, threads, FW.total_bytes, st>>>(p, FW);
+        break;
+      case SUS_VARIANT_TAGGING:
+        if (int rc = allow_big_smem(k_step_flat_ws<SUS_VARIANT_TAGGING>, FW.total_bytes)) return rc;
+        k_step_flat_ws<SUS_VARIANT_TAGGING><<<gr, threads, FW.total_bytes, st>>>(p, FW);
+        break;
+      default:
+        if (p.c.A == 5 && p.c.J == 0) {  // the reference's training shape: compile-time agent / job counts
+          if (int rc = allow_big_smem(k_step_flat_ws<SUS_VARIANT_TRAINING_GROUND, 5, 0>, FW.total_bytes)) return rc;
+          k_step_flat_ws<SUS_VARIANT_TRAINING_GROUND, 5, 0><<<gr, threads, FW.total_bytes, st>>>(p, FW);
+        } else {
+          if (int rc = allow_big_smem(k_step_flat_ws<SUS_VARIANT_TRAINING_GROUND>, FW.total_bytes)) return rc;
+          k_step_flat_ws<SUS_VARIANT_TRAINING_GROUND><<<gr, threads, FW.total_bytes, st>>>(p, FW);
+        }
+        break;
+    }
+    return after_launch("k_step_flat_ws");
   }
   FlatStage FS;
   if (want_staged_flat() && enc &&

@@ -167,6 +167,23 @@ struct ByteRow {
   __device__ __forceinline__ void put(int p, int v) const { r[p] = (uint8_t)(v + (int)kByteRowBias); }
   __device__ __forceinline__ void putf(int, float) const {}  // no float-valued component is ever staged as bytes
 };
+// RecordRow: a flat row as the short list of its NON-ZERO values, for the warp-specialised Flat kernel (k_step_flat_ws): the
+// compute warp leaves K 16-bit entries per env -- float offset inside the row (10 bits) | value as 6-bit two's complement
+// (every flat component but the scent one is an integer with |v| <= 30) -- prefilled with 0xffff = "no entry"; an emitter
+// warp sets those values in a persistently-zero float tile, bulk-stores the tile and clears them again.
+struct RecordRow {
+  static constexpr bool kPrefilledZero = true;
+  uint16_t* __restrict__ rec;
+  int* cnt;
+  int base, K;
+  __device__ __forceinline__ void put(int p, int v) const {
+    if (v != 0 && *cnt < K) rec[(*cnt)++] = (uint16_t)((uint32_t)(base + p) | (((uint32_t)v & 63u) << 10));
+  }
+  __device__ __forceinline__ void putf(int, float) const {}
+};
+constexpr uint32_t kRecordNone = 0xffffu;
+__device__ __forceinline__ float record_value(uint32_t ent) { return (float)((int)(((ent >> 10) & 63u) ^ 32u) - 32); }
+
 // float value of byte k of a word of a ByteRow: the byte becomes the low mantissa bits of 2^23, minus (2^23 + bias)
 __device__ __forceinline__ float byte_row_value(uint32_t w, int k) {
   return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)k)) - (8388608.0f + (float)kByteRowBias);
@@ -281,6 +298,14 @@ template <typename RowT, typename Elem>
 __device__ __forceinline__ void flat_row(const DevConfig& c, const DevEncode& enc, const GridTables& tb, const ObsState& o,
                                          Elem* __restrict__ row) {
   for (int q = 0; q < enc.n_components; ++q) row += flat_component(c, tb, o, enc.components[q], RowT{row});
+}
+
+// all components of a flat row as a RecordRow (entries in component order); returns the number of entries written
+__device__ __forceinline__ int flat_row_record(const DevConfig& c, const DevEncode& enc, const GridTables& tb, const ObsState& o,
+                                               uint16_t* __restrict__ rec, int K) {
+  int cnt = 0, base = 0;
+  for (int q = 0; q < enc.n_components; ++q) base += flat_component(c, tb, o, enc.components[q], RecordRow{rec, &cnt, base, K});
+  return cnt;
 }
 
 // Encode the 32 items a warp owns (item = item0 + lane; `cnt` of them exist, `have` says whether this

@@ -91,8 +91,31 @@ def test_episodic_metric_handler_from_stats(S, tmp_path):
     m.save_metrics(p)
     import json
 
+    # metrics.json: the reference's schema, {metric name: list} for all 13 metrics (metrics.py:88-90)
     d = json.loads(p.read_text())
-    assert d["episodes"] == 10 and d["truncated_episodes"] == 1 and d["totals"]["completed_jobs"] == 30
+    assert set(d) == {str(x.value) for x in S.SusMetrics} and d["crew_won"] == [0.6] and d["total_time_steps"] == [90.0]
+    # the exact totals live in the sidecar
+    t = json.loads((tmp_path / "metrics_totals.json").read_text())
+    assert t["episodes"] == 10 and t["truncated_episodes"] == 1 and t["totals"]["completed_jobs"] == 30
+    # per-interval lists: means over the episodes finished in each interval
+    m2 = S.EpisodicMetricHandler()
+    assert m2.log_interval(torch.tensor([10, 6, 4, 20, 30, 2, 1, 0, 900, 1]), [5.0, -3.0]) == 10
+    assert m2.log_interval(torch.tensor([30, 16, 14, 50, 70, 4, 1, 0, 2900, 3]), [15.0, -13.0]) == 20
+    assert m2.log_interval(torch.tensor([30, 16, 14, 50, 70, 4, 1, 0, 2900, 3]), [15.0, -13.0]) == 0  # nothing finished: no entry
+    assert m2.metrics[S.SusMetrics.CREW_WON] == [0.6, 0.5] and m2.metrics[S.SusMetrics.AVG_CREW_RETURNS] == [-0.3, -0.5]
+    assert m2.compute()[S.SusMetrics.CREW_WON] == 16 / 30 and m2.compute()[S.SusMetrics.AVG_IMPOSTER_RETURNS] == 0.5
+    m2.set({"imposter_loss": [1.0, 3.0], "crew_loss": [0.0, 0.0]})
+    m2.save_metrics(p)
+    from oracle import ref_harness as H
+
+    if H.reference_available():  # the reference's own handler loads the file and averages every key (metrics.py:84-95)
+        H.import_reference()
+        from src.metrics import EpisodicMetricHandler as Ref
+
+        r = Ref()
+        r.load_metrics(p)
+        avg = r.compute()
+        assert len(avg) == 13 and avg["crew_won"] == 0.55 and avg["imposter_loss"] == 2.0
 
 
 _GRAD_WORKER = r'''

@@ -106,7 +106,13 @@ def main():
                           "train_steps": len(losses), "last_losses": losses[-1],
                           "episodes": int(stats[0]), "imposter_win_rate": float(stats[2]) / max(int(stats[0]), 1)}))
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graphs hold NCCL work; tearing the communicator down with them alive hung the 8-GPU run at exit (the
+        # measurement had finished).  Drop the graphs, drain the device, meet at a barrier and leave without the destructor.
+        loop._g_iter = loop._g_train = None
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
