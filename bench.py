@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the BASELINE configs[1], [2], cfg4-alt and small-batch extras")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the cpu_baseline sample")
     ap.add_argument("--reference-sample", type=float, default=None, help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -373,6 +374,93 @@ def bind_to_gpu_numa_node(torch_device):
         pass
 
 
+# ------------------------------------------------------------------------------------------------ extras
+def other_configs(S, dev, rank, K, peak):
+    """Not bench lines (BASELINE configs[1], [2] and the Flat recipe are parity-test cases): the fused kernels of the other
+    configurations timed the same way -- CUDA events around the step launch, actions from `sample_actions()` in HBM."""
+    import torch
+
+    def timed(env, feat, n_steps, graph_steps=0):
+        env.emit_next_states = False
+        env.reset()
+        for _ in range(5):
+            env.step(env.sample_actions(), featurizer=feat)
+        torch.cuda.synchronize(dev)
+        evs = []
+        for _ in range(n_steps):
+            a = env.sample_actions()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); env.step(a, featurizer=feat); e.record()
+            evs.append((s, e))
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n_steps):
+            env.step(env.sample_actions(), featurizer=feat)
+        t1.record()
+        torch.cuda.synchronize(dev)
+        ms = sorted(s.elapsed_time(e) for s, e in evs)
+        return ms[len(ms) // 2], t0.elapsed_time(t1) / n_steps
+
+    out = {}
+    N = 1 << 20
+    # cfg4-alt: ImposterTrainingGround 1v4 + FlatFeaturizer(OneHot + AliveCrew + ClosestAliveCrew) = the reference's training recipe
+    env = S.BatchedImposterTrainingGround(n_crew=4, n_jobs=0, time_step_reward=0, kill_reward=-3, sabotage_reward=0,
+                                          end_of_game_reward=0, num_envs=N, seed=1234, env_id_base=rank * N, device=dev)
+    feat = S.FlatFeaturizer(env, S.CompositeFeaturizer([S.OneHotAgentPositionFeaturizer(env), S.AliveCrewFeaturizer(env),
+                                                        S.ClosestAliveCrewFeaturizer(env)]))
+    k_ms, step_ms = timed(env, feat, K)
+    gbs = 453 * N / (k_ms * 1e-3) / 1e9
+    out["cfg4alt_itg_1v4_flat98"] = {"envs": N, "kernel": "k_step_flat (fused step + Flat-98 encode, byte-staged rows)", "kernel_ms": k_ms,
+                                     "algorithmic_bytes_per_env_step": 453, "achieved_gbs": gbs, "frac_of_hbm_copy_peak": gbs / peak,
+                                     "env_steps_per_s_with_sampler": N / (step_ms * 1e-3)}
+    del env, feat
+    # BASELINE configs[3] at its smallest sweep point: Global features at 65 536 envs
+    n = 65536
+    env = S.BatchedFourRoomEnv(1, 4, 5, num_envs=n, seed=1234, device=dev)
+    feat = S.GlobalFeaturizer(env)
+    k_ms, step_ms = timed(env, feat, K)
+    gbs = ALGO_BYTES_STEP_ENCODE * n / (k_ms * 1e-3) / 1e9
+    out["cfg4_global_65536_envs"] = {"envs": n, "kernel_ms": k_ms, "achieved_gbs": gbs, "frac_of_hbm_copy_peak": gbs / peak,
+                                     "env_steps_per_s_with_sampler": n / (step_ms * 1e-3)}
+    # opt-in byte planes (SUS_ENCODE_PLANES_U8): same step + Global encode with one byte per plane cell; its OWN algorithmic
+    # bytes (82 step + 567 planes + 300 non-spatial = 949 B per env-step) -- never folded into roofline.frac
+    N8 = 1 << 20
+    env = S.BatchedFourRoomEnv(1, 4, 5, num_envs=N8, seed=1234, env_id_base=rank * N8, device=dev)
+    feat = S.GlobalFeaturizer(env, plane_dtype=torch.uint8)
+    k_ms, step_ms = timed(env, feat, K)
+    out["cfg4_global_byte_planes_opt_in"] = {"envs": N8, "kernel_ms": k_ms, "algorithmic_bytes_per_env_step": 949,
+                                             "achieved_gbs": 949 * N8 / (k_ms * 1e-3) / 1e9,
+                                             "env_steps_per_s_with_sampler": N8 / (step_ms * 1e-3),
+                                             "what": "GlobalFeaturizer(env, plane_dtype=torch.uint8): uint8 planes for a consumer that casts in its first layer"}
+    del env, feat
+    # BASELINE configs[2]: tagging 1v2, 5 jobs, 65 536 envs per GPU, step only (issue / latency bound: < 100 B per env-step)
+    env = S.BatchedFourRoomEnvWithTagging(1, 2, 5, num_envs=n, seed=1234, device=dev)
+    k_ms, step_ms = timed(env, None, K)
+    out["cfg3_tagging_1v2_65536_envs_step_only"] = {"envs": n, "kernel_ms": k_ms, "env_steps_per_s_with_sampler": n / (step_ms * 1e-3),
+                                                   "algorithmic_gbs": 74 * n / (k_ms * 1e-3) / 1e9}
+    env.reset()
+    torch.cuda.synchronize(dev)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(); env.rollout(200); t1.record()
+    torch.cuda.synchronize(dev)
+    out["cfg3_tagging_1v2_65536_envs_step_only"]["rollout_env_steps_per_s"] = n * 200 / (t0.elapsed_time(t1) * 1e-3)
+    del env
+    # BASELINE configs[1]: ImposterTrainingGround 1v1 walled, 4096 envs on one GPU (launch-latency bound per step; one-launch rollout)
+    n = 4096
+    env = S.BatchedImposterTrainingGround(n_crew=1, n_jobs=0, time_step_reward=0, kill_reward=-3, sabotage_reward=0,
+                                          end_of_game_reward=0, num_envs=n, seed=1234, device=dev)
+    k_ms, step_ms = timed(env, None, K)
+    env.reset()
+    torch.cuda.synchronize(dev)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(); env.rollout(1000); t1.record()
+    torch.cuda.synchronize(dev)
+    out["cfg2_itg_1v1_wall_4096_envs_step_only"] = {"envs": n, "kernel_ms": k_ms, "env_steps_per_s_with_sampler": n / (step_ms * 1e-3),
+                                                   "rollout_env_steps_per_s": n * 1000 / (t0.elapsed_time(t1) * 1e-3)}
+    del env
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_b200_arm(args):
     import torch
@@ -450,19 +538,26 @@ def run_b200_arm(args):
     from sus_net_b200.memory import is_compressible
 
     compressible = is_compressible(feat._sp_buf)
+    # DRAM bytes per launch come from an ncu capture (profiles/traffic.json, written by tools/update_traffic.py); they are only
+    # reported while the library is the build the capture was made with (content hash of the CUDA sources + flags)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic_note = None
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            if int(tj.get("envs_per_launch", -1)) == N:
+            if tj.get("lib_hash") != B._source_hash():
+                traffic_note = "profiles/traffic.json was captured with another build of the library: traffic not reported"
+            elif int(tj.get("envs_per_launch", -1)) == N:
                 traffic = (tj if compressible else tj.get("uncompressed", {})).get("dram_bytes_per_launch")
-            stream_peak = tj.get("bulk_store_stream_gbs", {}).get("compressible" if compressible else "cudaMalloc")
+            stream_peak = tj.get("store_ceiling_gbs", {}).get("compressible" if compressible else "cudaMalloc")
         except Exception:  # noqa: BLE001
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_step_ws<BASE> (fused step + Global encode, warp-specialised TMA path)", "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_env_step": ALGO_BYTES_STEP_ENCODE, "peak_source": peak_src,
                 "feature_memory": "L2-compressible (cuMemCreate + COMP_GENERIC)" if compressible else "cudaMalloc"}
+    if traffic_note:
+        roofline["traffic_note"] = traffic_note
     if traffic:
         roofline["dram_gbs"] = traffic / (kern_ms * 1e-3) / 1e9
     if compressible:
@@ -472,7 +567,9 @@ def run_b200_arm(args):
                             "what binds the kernel then is the SM -> L2 store stream, see `store_stream`")
     if stream_peak:
         roofline["store_stream"] = {"peak": stream_peak, "frac": achieved / stream_peak, "unit": "GB/s",
-                                    "what": "bare cp.async.bulk tile-store stream into the same kind of memory (tools/micro/compressible_bench.cu)"}
+                                    "what": "best SM -> L2 store stream into the same kind of memory over every pattern of "
+                                            "tools/micro/store_ceiling_bench.cu (STG.128 at 8-64 warps/SM, bulk tiles of 9-36 KB with "
+                                            "1-4 in flight from 1-12 issuing warps, per-lane bulk issue)"}
 
     # extra (not the headline): the same step with the random policy fused into the step kernel (one launch)
     for _ in range(2):
@@ -499,6 +596,7 @@ def run_b200_arm(args):
     del a
     stats_local = env.episode_stats()
     del env
+    other = other_configs(S, dev, rank, K, peak) if world == 1 and not args.no_extra else None
 
     # ---- arm 2: end to end through the public API with host buffers
     e2e = None
@@ -603,6 +701,7 @@ def run_b200_arm(args):
             "extra": {"sample_actions_kernel_ms": sample_ms, "fused_random_policy_env_steps_per_s": fused_policy_value,
                       "step_only_env_steps_per_s": step_only_value,
                       "step_only_hbm_gbs_algorithmic": ALGO_BYTES_STEP_ONLY * step_only_value / world / 1e9,
+                      "other_configs": other,
                       "episode_stats": dict(zip(S.STAT_KEYS, [int(x) for x in stats.tolist()]))},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -118,10 +118,16 @@ enum SusFlatComponent {
   SUS_FC_COUNT = 13
 };
 
+/* SusEncodeSpec.flags.  SUS_ENCODE_PLANES_U8 (opt-in, no reference analogue): the spatial tensor of GLOBAL / PERSPECTIVE
+ * holds ONE BYTE per cell (0 / 1) instead of one float32 -- same shape, same [channel][x][y] order, 4x fewer bytes -- for a
+ * consumer that casts in its first layer.  The non-spatial tensor stays float32. */
+#define SUS_ENCODE_PLANES_U8 1
+
 typedef struct SusEncodeSpec {
   int32_t kind;         /* SusEncodeKind */
   int32_t n_components; /* SUS_ENCODE_FLAT only */
   int32_t components[SUS_MAX_FLAT_COMPONENTS];
+  int32_t flags;        /* 0, or SUS_ENCODE_PLANES_U8 */
 } SusEncodeSpec;
 
 /* Output shapes of an encode spec for a config (host call, no GPU work):
@@ -151,7 +157,7 @@ typedef struct SusStepIO {
                               to (pre-reset env.imposter_idxs: the `imposters` replay column, replay_memory.py:42-44) */
   const SusEncodeSpec *encode; /* host pointer or NULL: fused encode of the state the NEXT action is
                               taken from (post auto-reset), written to spatial / non_spatial below */
-  float *spatial;          /* [views_s][N][spatial_floats]  */
+  void *spatial;           /* [views_s][N][spatial_floats] float32 (uint8 with SUS_ENCODE_PLANES_U8) */
   float *non_spatial;      /* [views_n][N][non_spatial_floats] */
   uint8_t *packed_out;     /* [N][result_bytes] compact result records (SusCompactLayout) INSTEAD of rewards / done /
                               truncated, which must then be NULL: what a host consumer pulls over PCIe per step */
@@ -237,13 +243,13 @@ int sus_env_export_imposter_mask(sus_env_t env, uint8_t *out, void *stream);
 int sus_env_export_metrics(sus_env_t env, int64_t *out, void *stream);
 
 /* SequenceStateFeaturizer.fit + generate_featurized_states on the envs' CURRENT states, T = 1.  Kernel K2. */
-int sus_env_encode(sus_env_t env, const SusEncodeSpec *spec /*host*/, float *spatial, float *non_spatial,
+int sus_env_encode(sus_env_t env, const SusEncodeSpec *spec /*host*/, void *spatial, float *non_spatial,
                    void *stream);
 /* SequenceStateFeaturizer.fit on a (B, T, S) batch of flattened states (train.py:70-74,346-348):
  * n_items = B*T rows of S values, dtype SUS_F32 / SUS_F64 / SUS_I64 (floats are truncated like
  * gymnasium.spaces.unflatten does).  Output item order = row order, so (B,T,...) views are free. */
 int sus_encode_from_flat(const SusConfig *cfg /*host*/, const SusEncodeSpec *spec /*host*/, const void *states,
-                         int32_t dtype, int64_t n_items, float *spatial, float *non_spatial, int device,
+                         int32_t dtype, int64_t n_items, void *spatial, float *non_spatial, int device,
                          void *stream);
 
 /* Finished-episode accumulators (SusStatIndex) of this handle since creation (or the last clear), int64[10].
@@ -342,6 +348,26 @@ typedef struct SusPolicyIO {
   void *actions;
 } SusPolicyIO;
 int sus_env_select_actions(sus_env_t env, const SusPolicyIO *io /*host*/, void *stream);
+
+/* Q-network inference for the reference's MLP estimator (src/models/dqn.py:72-108: `make_mlp`, a Linear + activation stack on
+ * the flattened non-spatial features; train.py:367-370,378-381 evaluate it per agent per step): out = MLP(x) for n_rows rows in
+ * ONE launch, activations resident in shared memory, fp32 FFMA (same arithmetic as the float32 reference up to summation order).
+ * weight[l] is [dims[l+1]][dims[l]] row-major (torch.nn.Linear.weight), bias[l] [dims[l+1]] or NULL, alpha[l] the single PReLU
+ * slope after layer l (torch.nn.PReLU(), num_parameters = 1) -- DEVICE pointers to the live parameters, nothing is copied.
+ * The activation follows every layer but the last.  SUS_ERR_UNSUPPORTED if two adjacent widths do not fit in shared memory. */
+#define SUS_MLP_MAX_LAYERS 8
+enum SusActivation { SUS_ACT_NONE = 0, SUS_ACT_RELU = 1, SUS_ACT_PRELU = 2 };
+typedef struct SusMlpSpec {
+  int32_t n_layers;
+  int32_t activation;                       /* SusActivation */
+  int32_t dims[SUS_MLP_MAX_LAYERS + 1];     /* dims[0] = input width ... dims[n_layers] = outputs */
+  int32_t reserved;
+  const float *weight[SUS_MLP_MAX_LAYERS];
+  const float *bias[SUS_MLP_MAX_LAYERS];
+  const float *alpha[SUS_MLP_MAX_LAYERS];
+} SusMlpSpec;
+int sus_mlp_forward(const SusMlpSpec *spec /*host*/, const float *x /*[n_rows][dims[0]]*/, int64_t n_rows,
+                    float *out /*[n_rows][dims[n_layers]]*/, int device, void *stream);
 
 /* T-deep sequences of ENCODED features (train.py:318-322,388-389,440-445 keep them as raw states and re-encode all T
  * every iteration): seq_out[r][t] = newest[r] if t == T-1 or env (r mod n_envs)'s episode just ended (done | truncated),

@@ -45,6 +45,7 @@ from .train import (  # noqa: F401
     train_batched,
 )
 from .compact import CompactProtocol  # noqa: F401
+from .mlp import FusedMLP  # noqa: F401
 
 # reference class names, for `from sus_net_b200 import FourRoomEnv` style drop-in use
 FourRoomEnv = BatchedFourRoomEnv

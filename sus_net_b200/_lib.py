@@ -10,6 +10,7 @@ SUS_OK, SUS_ERR_INVALID_ARGUMENT, SUS_ERR_UNSUPPORTED, SUS_ERR_CUDA, SUS_ERR_INV
 VARIANT_BASE, VARIANT_TAGGING, VARIANT_TRAINING_GROUND = 0, 1, 2
 U8, I32, I64, F32, F64, PACKED = 0, 1, 2, 3, 4, 5
 ENCODE_NONE, ENCODE_GLOBAL, ENCODE_PERSPECTIVE, ENCODE_FLAT = 0, 1, 2, 3
+ENCODE_PLANES_U8 = 1
 MAX_AGENTS, MAX_JOBS, N_METRICS, N_STATS, MAX_FLAT_COMPONENTS = 8, 8, 8, 10, 16
 ABI_VERSION = 2
 
@@ -21,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "sus_env_get_ticks", "sus_env_set_ticks", "sus_env_state_arrays", "sus_env_debug_inject_words",
     "sus_launch_count", "sus_replay_push", "sus_env_rollout", "sus_env_track_returns", "sus_env_return_sums",
     "sus_env_device_ticks", "sus_alloc_compressible", "sus_free_compressible", "sus_compact_layout", "sus_reward_lut",
-    "sus_env_select_actions", "sus_seq_roll", "sus_env_aux_arrays",
+    "sus_env_select_actions", "sus_seq_roll", "sus_env_aux_arrays", "sus_mlp_forward",
 )
 
 
@@ -38,7 +39,8 @@ class SusConfig(C.Structure):
 
 
 class SusEncodeSpec(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("n_components", C.c_int32), ("components", C.c_int32 * MAX_FLAT_COMPONENTS)]
+    _fields_ = [("kind", C.c_int32), ("n_components", C.c_int32), ("components", C.c_int32 * MAX_FLAT_COMPONENTS),
+                ("flags", C.c_int32)]
 
 
 class SusEncodeShape(C.Structure):
@@ -70,6 +72,16 @@ class SusReplayPush(C.Structure):
         ("states", C.c_void_p), ("r_actions", C.c_void_p), ("r_rewards", C.c_void_p), ("next_states", C.c_void_p),
         ("r_dones", C.c_void_p), ("r_imposters", C.c_void_p), ("idx_dev", C.c_void_p),
     ]
+
+
+MLP_MAX_LAYERS = 8
+ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+
+
+class SusMlpSpec(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("activation", C.c_int32), ("dims", C.c_int32 * (MLP_MAX_LAYERS + 1)),
+                ("reserved", C.c_int32), ("weight", C.c_void_p * MLP_MAX_LAYERS), ("bias", C.c_void_p * MLP_MAX_LAYERS),
+                ("alpha", C.c_void_p * MLP_MAX_LAYERS)]
 
 
 class SusPolicyIO(C.Structure):
@@ -134,6 +146,7 @@ def lib():
         "sus_replay_push": ([C.POINTER(SusReplayPush), C.c_int, vp], C.c_int),
         "sus_env_select_actions": ([vp, C.POINTER(SusPolicyIO), vp], C.c_int),
         "sus_seq_roll": ([vp, vp, vp, vp, vp, i64, i64, i32, i32, C.c_int, vp], C.c_int),
+        "sus_mlp_forward": ([C.POINTER(SusMlpSpec), vp, i64, vp, C.c_int, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)

@@ -81,7 +81,7 @@ struct StepParams {
   float* next_flat;
   long long* metrics;
   int16_t* imposters;
-  float* spatial;
+  void* spatial;  // float planes, or uint8_t planes with SUS_ENCODE_PLANES_U8
   float* non_spatial;
   const uint32_t* inj_step;
   const uint32_t* inj_reset;
@@ -117,7 +117,7 @@ struct EncodeParams {
   DevEncode enc;
   StateArrays st;      // k_encode_env
   const void* rows;    // k_encode_rows
-  float* spatial;
+  void* spatial;
   float* non_spatial;
   int64_t n_items;
 };
@@ -771,18 +771,19 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1) k_step_tma(const __grid_
 
 // One plane sub-tile (8 envs) of the emitter warp: retire the store that last used this tile, clear the ones it
 // carried, set the new ones from the group's plane records with all 32 lanes, hand the tile to the TMA engine.
-template <int TE>  // envs per plane tile: 8 or 16
+// T: the plane element type -- float (the reference's tensors) or uint8_t (opt-in compact planes, SUS_ENCODE_PLANES_U8).
+template <int TE, typename T>  // envs per plane tile: 8 or 16
 struct EmitterTile {
   static constexpr int NE = TE / 2;  // plane entries per lane: TE envs x 16 entries over 32 lanes
-  float* tile;
-  uint32_t prev[NE];  // float indices this lane set in the tile (0xffffffff = none)
+  T* tile;
+  uint32_t prev[NE];  // element indices this lane set in the tile (0xffffffff = none)
   bool inflight;
 };
 
-template <int TE, bool PERSPECTIVE>
-__device__ __forceinline__ void emit_sub(EmitterTile<TE>& t, EmitterTile<TE>& other, int& last_commit, int my_id,
-                                         const uint16_t* po, int g0, int cnt, int k, int A, int R, float* gdst, int lane) {
-  constexpr int NE = EmitterTile<TE>::NE;
+template <int TE, bool PERSPECTIVE, typename T>
+__device__ __forceinline__ void emit_sub(EmitterTile<TE, T>& t, EmitterTile<TE, T>& other, int& last_commit, int my_id,
+                                         const uint16_t* po, int g0, int cnt, int k, int A, int R, T* gdst, int lane) {
+  constexpr int NE = EmitterTile<TE, T>::NE;
   if (t.inflight) {
     if (lane == 0) {
       if (last_commit != my_id) bulk_wait_read_all_but_newest();  // the newest group reads the other tile
@@ -794,7 +795,7 @@ __device__ __forceinline__ void emit_sub(EmitterTile<TE>& t, EmitterTile<TE>& ot
   __syncwarp();
 #pragma unroll
   for (int r = 0; r < NE; ++r)
-    if (t.prev[r] != 0xffffffffu) t.tile[t.prev[r]] = 0.0f;
+    if (t.prev[r] != 0xffffffffu) t.tile[t.prev[r]] = (T)0;
   const int gc = cnt - g0 < TE ? cnt - g0 : TE;
   const int el = lane & (TE - 1);
   const uint16_t* rec = po + (g0 + el) * 16 + lane / TE;
@@ -809,7 +810,7 @@ __device__ __forceinline__ void emit_sub(EmitterTile<TE>& t, EmitterTile<TE>& ot
         if (k > 0 && q < A) off[r] += (uint32_t)((persp_channel_of_agent(k, q) - q) * 81);  // view k's channel order
       }
       const uint32_t idx = (uint32_t)(el * R) + off[r];
-      t.tile[idx] = 1.0f;
+      t.tile[idx] = (T)1;
       t.prev[r] = idx;
     } else {
       t.prev[r] = 0xffffffffu;
@@ -817,7 +818,7 @@ __device__ __forceinline__ void emit_sub(EmitterTile<TE>& t, EmitterTile<TE>& ot
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (drain(gdst, t.tile, (uint32_t)(gc * R * 4), lane)) {
+  if (drain(gdst, t.tile, (uint32_t)(gc * R * (int)sizeof(T)), lane)) {
     if (lane == 0) bulk_commit();
     t.inflight = true;
     last_commit = my_id;
@@ -825,14 +826,14 @@ __device__ __forceinline__ void emit_sub(EmitterTile<TE>& t, EmitterTile<TE>& ot
 }
 
 // the emitter warp's loop over the groups its CTA's compute warps produce
-template <int TE, bool PERSPECTIVE>
-__device__ __forceinline__ void emitter_loop(int A, int R, int64_t N, float* __restrict__ spatial, const WsLayout& L,
+template <int TE, bool PERSPECTIVE, typename T>
+__device__ __forceinline__ void emitter_loop(int A, int R, int64_t N, T* __restrict__ spatial, const WsLayout& L,
                                              uint8_t* dyn_smem, uint64_t* bars, int64_t n_groups, int64_t g_stride, int lane) {
-  constexpr int NE = EmitterTile<TE>::NE;
+  constexpr int NE = EmitterTile<TE, T>::NE;
   const int CW = L.compute_warps;
-  EmitterTile<TE> t0, t1;
-  t0.tile = reinterpret_cast<float*>(dyn_smem);
-  t1.tile = reinterpret_cast<float*>(dyn_smem + L.tile_bytes);
+  EmitterTile<TE, T> t0, t1;
+  t0.tile = reinterpret_cast<T*>(dyn_smem);
+  t1.tile = reinterpret_cast<T*>(dyn_smem + L.tile_bytes);
   t0.inflight = t1.inflight = false;
 #pragma unroll
   for (int r = 0; r < NE; ++r) t0.prev[r] = t1.prev[r] = 0xffffffffu;
@@ -851,11 +852,11 @@ __device__ __forceinline__ void emitter_loop(int A, int R, int64_t N, float* __r
       const int cnt = rem < 32 ? (int)rem : 32;
       const uint16_t* po = reinterpret_cast<const uint16_t*>(slot + L.po_off);
       for (int k = 0; k < sp_views; ++k) {
-        float* gbase = spatial + ((int64_t)k * N + e0) * R;
+        T* gbase = spatial + ((int64_t)k * N + e0) * R;
         for (int g0 = 0; g0 < cnt; g0 += 2 * TE) {
-          emit_sub<TE, PERSPECTIVE>(t0, t1, last_commit, 0, po, g0, cnt, k, A, R, gbase + (int64_t)g0 * R, lane);
+          emit_sub<TE, PERSPECTIVE, T>(t0, t1, last_commit, 0, po, g0, cnt, k, A, R, gbase + (int64_t)g0 * R, lane);
           if (g0 + TE < cnt)
-            emit_sub<TE, PERSPECTIVE>(t1, t0, last_commit, 1, po, g0 + TE, cnt, k, A, R, gbase + (int64_t)(g0 + TE) * R, lane);
+            emit_sub<TE, PERSPECTIVE, T>(t1, t0, last_commit, 1, po, g0 + TE, cnt, k, A, R, gbase + (int64_t)(g0 + TE) * R, lane);
         }
       }
       __syncwarp();
@@ -865,15 +866,22 @@ __device__ __forceinline__ void emitter_loop(int A, int R, int64_t N, float* __r
   if (lane == 0) bulk_wait_all();
 }
 
-__device__ __forceinline__ void emitter_dispatch(bool persp, int A, int R, int64_t N, float* spatial, const WsLayout& L,
-                                                 uint8_t* dyn_smem, uint64_t* bars, int64_t n_groups, int64_t g_stride,
-                                                 int lane) {
+__device__ __forceinline__ void emitter_dispatch(bool persp, bool planes_u8, int A, int R, int64_t N, void* spatial,
+                                                 const WsLayout& L, uint8_t* dyn_smem, uint64_t* bars, int64_t n_groups,
+                                                 int64_t g_stride, int lane) {
+  if (planes_u8) {  // 16-env tiles only: 16 x (A+2) x 81 bytes is a multiple of 16, 8 x is not
+    uint8_t* sp = static_cast<uint8_t*>(spatial);
+    if (persp) emitter_loop<16, true, uint8_t>(A, R, N, sp, L, dyn_smem, bars, n_groups, g_stride, lane);
+    else emitter_loop<16, false, uint8_t>(A, R, N, sp, L, dyn_smem, bars, n_groups, g_stride, lane);
+    return;
+  }
+  float* sp = static_cast<float*>(spatial);
   if (L.tile_envs == 16) {
-    if (persp) emitter_loop<16, true>(A, R, N, spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
-    else emitter_loop<16, false>(A, R, N, spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+    if (persp) emitter_loop<16, true, float>(A, R, N, sp, L, dyn_smem, bars, n_groups, g_stride, lane);
+    else emitter_loop<16, false, float>(A, R, N, sp, L, dyn_smem, bars, n_groups, g_stride, lane);
   } else {
-    if (persp) emitter_loop<8, true>(A, R, N, spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
-    else emitter_loop<8, false>(A, R, N, spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+    if (persp) emitter_loop<8, true, float>(A, R, N, sp, L, dyn_smem, bars, n_groups, g_stride, lane);
+    else emitter_loop<8, false, float>(A, R, N, sp, L, dyn_smem, bars, n_groups, g_stride, lane);
   }
 }
 
@@ -951,7 +959,7 @@ __global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_step_ws(const __grid_co
     if (lane == 0) bulk_wait_all();
   } else if (warp == CW) {
     // ------------------------------------------------------------------ emitter warp
-    emitter_dispatch(p.enc.kind == SUS_ENCODE_PERSPECTIVE, A, R, p.N, p.spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+    emitter_dispatch(p.enc.kind == SUS_ENCODE_PERSPECTIVE, p.enc.planes_u8 != 0, A, R, p.N, p.spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
   }
 }
 
@@ -1174,7 +1182,7 @@ __global__ void __launch_bounds__(kWsMaxWarps * 32, 1) k_encode_ws(const __grid_
     }
     if (lane == 0) bulk_wait_all();
   } else if (warp == CW) {
-    emitter_dispatch(p.enc.kind == SUS_ENCODE_PERSPECTIVE, A, R, p.n_items, p.spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
+    emitter_dispatch(p.enc.kind == SUS_ENCODE_PERSPECTIVE, p.enc.planes_u8 != 0, A, R, p.n_items, p.spatial, L, dyn_smem, bars, n_groups, g_stride, lane);
   }
 }
 
@@ -1331,6 +1339,7 @@ int make_dev_encode(const SusConfig& c, const SusEncodeSpec* spec, DevEncode& d,
       return fail(SUS_ERR_INVALID_ARGUMENT, "Global/Perspective featurizers need n_jobs > 0");
     const int tags = c.variant == SUS_VARIANT_TAGGING ? A : 0;
     d.kind = spec->kind;
+    d.planes_u8 = (spec->flags & SUS_ENCODE_PLANES_U8) ? 1 : 0;
     sh.spatial_floats = (A + 2) * 81;
     sh.non_spatial_views = A;
     if (spec->kind == SUS_ENCODE_GLOBAL) { sh.spatial_views = 1; sh.non_spatial_floats = A + tags + J + A; }
@@ -1383,6 +1392,7 @@ bool want_tma() {
 
 // Per-warp staging layout; returns false if not even two warps fit (then the direct path is used).
 bool make_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool want_nf, int max_dyn_smem, TileLayout& L) {
+  if (enc.planes_u8) return false;  // byte planes: warp-specialised or direct path only
   const int views = enc.kind == SUS_ENCODE_NONE ? 0 : (enc.kind == SUS_ENCODE_FLAT ? 1 : c.A);
   TileLayout best = {};
   // tuning overrides (tools/kernel_sweep.py): SUSNET_TILE_G in {4, 8, 16}, SUSNET_TILE_WARPS in 2..8
@@ -1496,9 +1506,10 @@ bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool
   WsLayout t = {};
   const bool compute_bound = step && fast_sink && enc.kind == SUS_ENCODE_GLOBAL;
   const char* env_te = std::getenv("SUSNET_WS_TILE");
-  t.tile_envs = env_te ? (std::atoi(env_te) == 8 ? 8 : 16) : (compute_bound ? 8 : 16);
-  t.tile_bytes = align128((int64_t)t.tile_envs * enc.sp_floats * 4);
-  if (t.tile_envs == 16 && max_dyn_smem - 2048 - 2 * t.tile_bytes - 512 < 4 * (32 * 32 + align128((int64_t)c.A * 32 * enc.ns_floats * 4) + align128((int64_t)32 * c.A * rew_elem))) {
+  const int elem = enc.planes_u8 ? 1 : 4;
+  t.tile_envs = enc.planes_u8 ? 16 : (env_te ? (std::atoi(env_te) == 8 ? 8 : 16) : (compute_bound ? 8 : 16));
+  t.tile_bytes = align128((int64_t)t.tile_envs * enc.sp_floats * elem);
+  if (!enc.planes_u8 && t.tile_envs == 16 && max_dyn_smem - 2048 - 2 * t.tile_bytes - 512 < 4 * (32 * 32 + align128((int64_t)c.A * 32 * enc.ns_floats * 4) + align128((int64_t)32 * c.A * rew_elem))) {
     t.tile_envs = 8;  // big configs: fall back to 8-env tiles so that at least two compute warps fit
     t.tile_bytes = align128((int64_t)8 * enc.sp_floats * 4);
   }
@@ -1514,8 +1525,9 @@ bool make_ws_layout(const DevConfig& c, const DevEncode& enc, int rew_elem, bool
   const char* env_w = std::getenv("SUSNET_WS_WARPS");
   // encode-only launches: any count >= 5 is the same for Global (0.393-0.398 ms at 1 Mi rows); Perspective is best
   // with 5 (0.419 ms at 256 Ki rows against 0.427 with 7-8 and 0.459 with 11)
+  // byte planes (4x fewer plane bytes): the step arithmetic binds, so every compute warp that fits is used
   const int want_cw = env_w && std::atoi(env_w) > 0 ? std::atoi(env_w)
-                      : (!step ? (enc.kind == SUS_ENCODE_PERSPECTIVE ? 5 : cw) : (compute_bound ? 7 : 6));
+                      : (enc.planes_u8 ? cw : (!step ? (enc.kind == SUS_ENCODE_PERSPECTIVE ? 5 : cw) : (compute_bound ? 7 : 6)));
   if (want_cw < cw) cw = want_cw;
   if (cw < 2) return false;
   t.compute_warps = cw;
@@ -1538,6 +1550,15 @@ bool want_staged_flat() {
 bool want_ws() {
   const char* v = std::getenv("SUSNET_PATH");
   return !v || std::strcmp(v, "ws") == 0;
+}
+
+// Flat encodes: the warp-specialised record kernel (k_step_flat_ws) only when asked for.  Measured at 1 Mi envs, cfg4-alt
+// Flat-98 (profiles/r02_flat98_ws_sweep.jsonl): 0.0881 ms with 4 emitter + 28 compute warps against 0.0881 ms for the staged
+// bytes kernel (and 0.092-0.135 ms with fewer warps / emitters) -- halving the compute warps' instructions did not shorten a
+// group's latency, which is what binds both kernels, so the simpler non-persistent staged kernel stays the default.
+bool want_flat_ws() {
+  const char* v = std::getenv("SUSNET_PATH");
+  return v && std::strcmp(v, "ws") == 0;
 }
 
 unsigned persistent_grid(int64_t n_items, const TileLayout& L, int sms) {
@@ -1788,7 +1809,8 @@ static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
   // step-only launches move < 100 B per env and are latency/issue bound: the one-thread-per-env kernel with its
   // higher occupancy wins there (measured 14.6e9 vs 7.3e9 env-steps/s); the TMA path pays off once features are written
   WsLayout W;
-  if (want_ws() && enc && make_ws_layout(p.c, p.enc, io->rewards_dtype == SUS_F64 ? 8 : 4, io->next_flat != nullptr,
+  if ((want_ws() || (p.enc.planes_u8 && want_tma())) && enc &&
+      make_ws_layout(p.c, p.enc, io->rewards_dtype == SUS_F64 ? 8 : 4, io->next_flat != nullptr,
                                          di.max_dyn_smem, true, sus_internal_is_compressible(io->spatial) != 0, W)) {
     const int64_t groups = (e->N + 31) / 32;
     const int64_t ctas = (groups + W.compute_warps - 1) / W.compute_warps;
@@ -1811,7 +1833,7 @@ static int step_launch(sus_env_t e, const SusStepIO* io, void* stream) {
     return after_launch("k_step_ws");
   }
   FlatWsLayout FW;
-  if (want_ws() && enc && make_flat_ws_layout(p.c, p.enc, io->packed_out ? p.result_bytes : p.c.A * (io->rewards_dtype == SUS_F64 ? 8 : 4),
+  if (want_flat_ws() && enc && make_flat_ws_layout(p.c, p.enc, io->packed_out ? p.result_bytes : p.c.A * (io->rewards_dtype == SUS_F64 ? 8 : 4),
                                               io->next_flat != nullptr, di.max_dyn_smem, FW)) {
     const int64_t groups = (e->N + 31) / 32;
     const int64_t ctas = (groups + FW.compute_warps - 1) / FW.compute_warps;
@@ -2019,7 +2041,7 @@ int sus_env_export_metrics(sus_env_t e, int64_t* out, void* stream) {
   return after_launch("k_export_metrics");
 }
 
-int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float* non_spatial, void* stream) {
+int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, void* spatial, float* non_spatial, void* stream) {
   if (!e || !spec) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   DeviceGuard g(e->device);
   EncodeParams p;
@@ -2034,7 +2056,7 @@ int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float
   DeviceInfo di;
   if (int rc = device_info(e->device, di)) return rc;
   WsLayout W;
-  if (want_ws() && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, false, false, W)) {
+  if ((want_ws() || (p.enc.planes_u8 && want_tma())) && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, false, false, W)) {
     if (int rc = allow_big_smem(k_encode_ws<float, false>, W.total_bytes)) return rc;
     k_encode_ws<float, false><<<ws_grid(e->N, W, di.sms), (W.compute_warps + 1) * 32, W.total_bytes, (cudaStream_t)stream>>>(p, W);
     return after_launch("k_encode_ws");
@@ -2058,7 +2080,7 @@ int sus_env_encode(sus_env_t e, const SusEncodeSpec* spec, float* spatial, float
 }
 
 int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const void* states, int32_t dtype,
-                         int64_t n_items, float* spatial, float* non_spatial, int device, void* stream) {
+                         int64_t n_items, void* spatial, float* non_spatial, int device, void* stream) {
   if (!cfg || !spec) return fail(SUS_ERR_INVALID_ARGUMENT, "NULL argument");
   if (int rc = validate_config(*cfg)) return rc;
   if (n_items > 0 && !states) return fail(SUS_ERR_INVALID_ARGUMENT, "states is NULL");
@@ -2080,7 +2102,7 @@ int sus_encode_from_flat(const SusConfig* cfg, const SusEncodeSpec* spec, const 
   DeviceInfo di;
   if (int rc = device_info(device, di)) return rc;
   WsLayout W;
-  if (want_ws() && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, false, false, W)) {
+  if ((want_ws() || (p.enc.planes_u8 && want_tma())) && make_ws_layout(p.c, p.enc, 0, false, di.max_dyn_smem, false, false, W)) {
     const unsigned gr = ws_grid(n_items, W, di.sms), threads = (unsigned)(W.compute_warps + 1) * 32;
     if (dtype == SUS_F32) {
       if (int rc = allow_big_smem(k_encode_ws<float, true>, W.total_bytes)) return rc;

@@ -12,6 +12,7 @@ namespace susnet {
 
 struct DevEncode {
   int32_t kind, n_components, sp_floats, ns_floats;
+  int32_t planes_u8;  // SUS_ENCODE_PLANES_U8: the plane tensor holds one byte per cell instead of one float
   int32_t components[SUS_MAX_FLAT_COMPONENTS];
 };
 
@@ -35,9 +36,9 @@ __device__ __forceinline__ bool code_ok(uint32_t c) { return (c >> 4) <= 8u && (
 
 // agent / job planes of one item; `ch_of(i)` gives the channel agent i is shown in
 // (AgentPositionsFeaturizer component.py:90-100, JobFeaturizer component.py:116-127).
-template <typename ChannelOf>
-__device__ __forceinline__ void scatter_planes(const DevConfig& c, const ObsState& o, float* __restrict__ sp,
-                                               ChannelOf ch_of, float v) {
+template <typename ChannelOf, typename T>
+__device__ __forceinline__ void scatter_planes(const DevConfig& c, const ObsState& o, T* __restrict__ sp,
+                                               ChannelOf ch_of, T v) {
   const int A = c.A, J = c.J;
   for (int i = 0; i < A; ++i) {
     const uint32_t b = get_byte(o.pos, i);
@@ -312,10 +313,31 @@ __device__ __forceinline__ int flat_row_record(const DevConfig& c, const DevEnco
 // lane's item exists).  All 32 lanes must call this together.
 __device__ __forceinline__ void warp_encode(const DevConfig& c, const DevEncode& enc, const GridTables& tb,
                                             const ObsState& o, int64_t item0, int cnt, bool have, int64_t n_items,
-                                            float* __restrict__ spatial, float* __restrict__ non_spatial) {
+                                            void* __restrict__ spatial_any, float* __restrict__ non_spatial) {
   const int lane = threadIdx.x & 31;
   const int64_t item = item0 + lane;
   const int A = c.A;
+  if (enc.planes_u8 && (enc.kind == SUS_ENCODE_GLOBAL || enc.kind == SUS_ENCODE_PERSPECTIVE)) {
+    // one byte per cell (opt-in compact planes): zero the warp's rows bytewise, then scatter the ones
+    uint8_t* sp8 = static_cast<uint8_t*>(spatial_any);
+    const int R = enc.sp_floats;
+    const int views = enc.kind == SUS_ENCODE_GLOBAL ? 1 : A;
+    for (int k = 0; k < views; ++k) {
+      uint8_t* base = sp8 + ((int64_t)k * n_items + item0) * R;
+      for (int64_t i = lane; i < (int64_t)cnt * R; i += 32) base[i] = 0;
+    }
+    __syncwarp();
+    if (have) {
+      for (int k = 0; k < views; ++k)
+        scatter_planes(c, o, sp8 + ((int64_t)k * n_items + item) * R, [k](int i) { return persp_channel_of_agent(k, i); }, (uint8_t)1);
+      for (int k = 0; k < A; ++k) {
+        float* row = non_spatial + ((int64_t)k * n_items + item) * enc.ns_floats;
+        if (enc.kind == SUS_ENCODE_GLOBAL) global_ns_row(c, o, k, row); else persp_ns_row(c, o, k, row);
+      }
+    }
+    return;
+  }
+  float* __restrict__ spatial = static_cast<float*>(spatial_any);
   if (enc.kind == SUS_ENCODE_GLOBAL) {
     const int R = enc.sp_floats;
     warp_zero_fill(spatial + item0 * R, (int64_t)cnt * R, lane);

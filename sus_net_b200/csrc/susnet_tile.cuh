@@ -135,8 +135,9 @@ struct WarpEmitter {
 // `dense_open`: the caller already acquired the dense rows and issued (uncommitted) rewards / next_flat stores.
 __device__ __forceinline__ void warp_encode_tma(const DevConfig& c, const DevEncode& enc, const GridTables& tb,
                                                 WarpEmitter& em, const ObsState& o, int64_t item0, int cnt, bool have,
-                                                int64_t n_items, float* __restrict__ spatial,
+                                                int64_t n_items, void* __restrict__ spatial_any,
                                                 float* __restrict__ non_spatial, bool dense_open, bool dense_any) {
+  float* __restrict__ spatial = static_cast<float*>(spatial_any);  // (uint8 planes never take this path: make_layout refuses)
   const int lane = em.lane, A = c.A;
   const TileLayout& L = *em.L;
   const int F = enc.ns_floats, R = enc.sp_floats;

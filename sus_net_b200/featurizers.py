@@ -16,6 +16,7 @@ import torch
 
 from . import _lib as L
 from .env import StateFields, _ptr, _TORCH_TO_SUS
+from .memory import empty as empty_dev
 from .memory import empty_f32
 
 
@@ -149,7 +150,12 @@ class SequenceStateFeaturizer:
 
     _KIND = L.ENCODE_NONE
 
-    def __init__(self, env, clone_views=False, output_device=None):
+    def __init__(self, env, clone_views=False, output_device=None, plane_dtype=torch.float32):
+        """plane_dtype=torch.uint8 (opt-in, Global / Perspective only; no reference analogue): the spatial tensors hold one
+        byte per cell instead of one float32 -- same shape and order, 4x fewer bytes to write and to read back -- for a
+        network that casts in its first layer.  The returned spatial views are then uint8 tensors without `requires_grad`."""
+        assert plane_dtype in (torch.float32, torch.uint8)
+        self.plane_dtype = plane_dtype
         self.env = env
         self.state_size = env.flattened_state_size
         self.clone_views = clone_views  # True: every agent view owns its memory like the reference's .clone()
@@ -165,7 +171,8 @@ class SequenceStateFeaturizer:
         self.B = self.T = None
 
     def _make_spec(self):
-        return L.SusEncodeSpec(kind=self._KIND, n_components=0)
+        return L.SusEncodeSpec(kind=self._KIND, n_components=0,
+                               flags=L.ENCODE_PLANES_U8 if self.plane_dtype == torch.uint8 else 0)
 
     def _alloc(self, n_items):
         sh, dev = self._shape, self.env.device
@@ -173,7 +180,7 @@ class SequenceStateFeaturizer:
             if len(self._buffers) >= 4:
                 self._buffers.pop(next(iter(self._buffers)))
             # the output tensors are almost all zeros: L2-compressible memory where the device has it (memory.py)
-            sp = empty_f32((sh.spatial_views, n_items, sh.spatial_floats), dev) if sh.spatial_views else None
+            sp = empty_dev((sh.spatial_views, n_items, sh.spatial_floats), dev, self.plane_dtype) if sh.spatial_views else None
             ns = empty_f32((sh.non_spatial_views, n_items, sh.non_spatial_floats), dev)
             self._buffers[n_items] = (sp, ns)
         self._sp_buf, self._ns_buf = self._buffers[n_items]
@@ -192,7 +199,7 @@ class SequenceStateFeaturizer:
     def new_buffers(self, n_items):
         """A fresh (spatial, non_spatial) output pair for `n_items` items (callers that double-buffer, e.g. `HostStepper`)."""
         sh, dev = self._shape, self.env.device
-        sp = empty_f32((sh.spatial_views, n_items, sh.spatial_floats), dev) if sh.spatial_views else None
+        sp = empty_dev((sh.spatial_views, n_items, sh.spatial_floats), dev, self.plane_dtype) if sh.spatial_views else None
         return sp, empty_f32((sh.non_spatial_views, n_items, sh.non_spatial_floats), dev)
 
     def bind_buffers(self, sp, ns):
@@ -252,7 +259,7 @@ class SequenceStateFeaturizer:
             t = t.to(self.output_device)
         elif self.clone_views:
             t = t.clone()
-        return t.requires_grad_(True)
+        return t.requires_grad_(True) if t.is_floating_point() else t
 
 
 class GlobalFeaturizer(SequenceStateFeaturizer):
@@ -300,7 +307,7 @@ class FlatFeaturizer(SequenceStateFeaturizer):
 
     def _make_spec(self):
         codes = self.featurizer.codes()
-        spec = L.SusEncodeSpec(kind=self._KIND, n_components=len(codes))
+        spec = L.SusEncodeSpec(kind=self._KIND, n_components=len(codes), flags=0)
         for i, c in enumerate(codes):
             spec.components[i] = c
         return spec

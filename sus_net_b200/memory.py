@@ -23,9 +23,9 @@ class _Block:
     """Owner of one compressible allocation; tensors made from it keep it alive (torch holds a reference to the object
     that exports __cuda_array_interface__ until the storage dies) and the memory is unmapped when the last one goes."""
 
-    def __init__(self, lib, ptr, shape):
+    def __init__(self, lib, ptr, shape, typestr="<f4"):
         self._lib, self._ptr, self._pid = lib, ptr, os.getpid()
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
 
     def __del__(self):
         if os.getpid() != self._pid:  # a forked child (e.g. a DataLoader worker) must not touch the parent's CUDA context
@@ -45,8 +45,15 @@ def compressible_enabled():
 
 def empty_f32(shape, device):
     """Uninitialised float32 tensor of `shape` on `device`, in L2-compressible memory where that applies."""
+    return empty(shape, device, torch.float32)
+
+
+def empty(shape, device, dtype=torch.float32):
+    """Uninitialised float32 / uint8 tensor of `shape` on `device`, in L2-compressible memory where that applies."""
+    assert dtype in (torch.float32, torch.uint8)
+    typestr, itemsize = ("<f4", 4) if dtype == torch.float32 else ("|u1", 1)
     device = torch.device(device)
-    nbytes = 4 * int(np.prod(shape))
+    nbytes = itemsize * int(np.prod(shape))
     if compressible_enabled() and nbytes >= MIN_BYTES and device.index not in _unsupported:
         lib = L.lib()
         while _deferred and not torch.cuda.is_current_stream_capturing():
@@ -55,14 +62,14 @@ def empty_f32(shape, device):
         ptr = C.c_void_p()
         rc = lib.sus_alloc_compressible(device.index, nbytes, C.byref(ptr), None)
         if rc == L.SUS_OK:
-            t = torch.as_tensor(_Block(lib, ptr.value, shape), device=device)
+            t = torch.as_tensor(_Block(lib, ptr.value, shape, typestr), device=device)
             t._sus_compressible = True
             return t
         if rc != L.SUS_ERR_UNSUPPORTED:  # e.g. the driver refuses virtual-memory allocations in this container: say so once
             warnings.warn(f"sus_alloc_compressible failed ({lib.sus_last_error().decode()}); feature tensors of cuda:{device.index} "
                           "stay in ordinary device memory", RuntimeWarning, stacklevel=2)
         _unsupported.add(device.index)
-    return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+    return torch.empty(tuple(shape), dtype=dtype, device=device)
 
 
 def is_compressible(t):

@@ -104,10 +104,17 @@ class BatchedActor:
     `act_kernel` is the production path (no host sync, one selection kernel, graph-capturable); `act` / `act_grouped`
     are the torch-op restatements kept for comparison (same distribution; identical actions for eps == 0)."""
 
-    def __init__(self, env, imposter_model, crew_model, generator=None, dense=False):
+    def __init__(self, env, imposter_model, crew_model, generator=None, dense=False, fused_mlp=True):
+        """fused_mlp: evaluate Linear + PReLU / ReLU stacks (the reference's MLP estimator) with the one-launch inference kernel
+        (`sus_net_b200.mlp.FusedMLP`) in `act_kernel`; other modules, and everything in `act` / `act_grouped`, run as they are."""
         self.env, self.imposter_model, self.crew_model = env, imposter_model, crew_model
         self.generator, self.dense = generator, dense
         self._q_imp = self._q_crew = self._actions = self._eps = None
+        from .mlp import FusedMLP
+
+        self._infer = {}
+        for name, m in (("imp", imposter_model), ("crew", crew_model)):
+            self._infer[name] = FusedMLP(m) if (fused_mlp and FusedMLP.supports(m)) else m
 
     # ---- production path
     @torch.no_grad()
@@ -127,26 +134,27 @@ class BatchedActor:
                 return torch.zeros(N, T, 1, device=dev)  # FlatFeaturizer's spatial placeholder (model_ready.py:362)
             return t[0] if t.shape[0] == 1 else t[k]
 
+        imp_net, crew_net = self._infer["imp"], self._infer["crew"]
         if self.imposter_model is not None:
             if env.n_imposters == 1:
                 if ns.shape[0] == 1 and (sp is None or sp.shape[0] == 1):
-                    q = self.imposter_model(view(sp, 0), ns[0])  # every view is identical (Flat)
+                    q = imp_net(view(sp, 0), ns[0])  # every view is identical (Flat)
                 else:
                     if imposter_index is None:
                         imposter_index = torch.argmax(env.imposter_mask_batch.to(torch.uint8), dim=1)
                     rows = torch.arange(N, device=dev)
                     spv = view(sp, 0) if (sp is None or sp.shape[0] == 1) else sp[imposter_index, rows]
-                    q = self.imposter_model(spv, ns[imposter_index, rows])
+                    q = imp_net(spv, ns[imposter_index, rows])
                 io.imposter_per_view = 0
             else:
-                q = torch.stack([self.imposter_model(view(sp, k), view(ns, k)) for k in range(A)])
+                q = torch.stack([imp_net(view(sp, k), view(ns, k)) for k in range(A)])
                 io.imposter_per_view = 1
             q = q.float().contiguous()
             assert q.shape[-1] == env.n_imposter_actions
             keep.append(q)
             io.q_imposter = q.data_ptr()
         if self.crew_model is not None:
-            q = torch.stack([self.crew_model(view(sp, k), view(ns, k)) for k in range(A)]).float().contiguous()
+            q = torch.stack([crew_net(view(sp, k), view(ns, k)) for k in range(A)]).float().contiguous()
             assert q.shape[-1] == env.n_crew_actions
             keep.append(q)
             io.q_crew = q.data_ptr()
@@ -398,7 +406,7 @@ class BatchedTrainingLoop:
     replay them (device-resident env ticks, replay index / size and ε make the replays advance like eager calls)."""
 
     def __init__(self, env, replay_buffer, featurizer, imposter_model, crew_model, trainer, scheduler, batch_size=1024,
-                 train_step_interval=5, target_update_interval=1000, use_graphs=False, imposter_index=None):
+                 train_step_interval=5, target_update_interval=1000, use_graphs=False, imposter_index=None, fused_mlp=True):
         self.env, self.buf, self.feat, self.trainer, self.sched = env, replay_buffer, featurizer, trainer, scheduler
         self.imposter_model, self.crew_model = imposter_model, crew_model
         self.batch_size, self.train_every, self.target_every = batch_size, train_step_interval, target_update_interval
@@ -406,7 +414,7 @@ class BatchedTrainingLoop:
         dev = env.device
         self.imposter_target = _copy_model(imposter_model, dev)
         self.crew_target = _copy_model(crew_model, dev)
-        self.actor = BatchedActor(env, imposter_model, crew_model)
+        self.actor = BatchedActor(env, imposter_model, crew_model, fused_mlp=fused_mlp)
         if use_graphs:
             env.device_ticks(True)
         replay_buffer.attach(env, static_buffers=use_graphs)

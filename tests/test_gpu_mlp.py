@@ -1,0 +1,75 @@
+"""GPU: the one-launch MLP inference kernel (`sus_mlp_forward`, row f2: the Q-network evaluation of the acting loop,
+src/train.py:367-370 on src/models/dqn.py:72-108) against the torch module it restates: same float32 arithmetic up to
+summation order (tolerance 2e-5 relative to the row's largest |Q|, stated here; the reference's own CPU BLAS differs from
+any GPU by as much)."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+
+def make(dims, act):
+    layers = []
+    for i, d in enumerate(dims[:-1]):
+        layers += [nn.Linear(d, dims[i + 1]), act()]
+    return nn.Sequential(*layers[:-1])
+
+
+class RefMLP(nn.Module):  # dqn.py:72-93
+    def __init__(self, dims, act=nn.PReLU):
+        super().__init__()
+        self.model = make(dims, act)
+
+    def forward(self, spatial_x, non_spatial_x):
+        return self.model(non_spatial_x.view(spatial_x.size(0), -1))
+
+
+@pytest.mark.parametrize("dims,act,rows", [
+    ([98, 256, 128, 64, 16, 6], nn.PReLU, 131072), ([98, 256, 128, 64, 16, 6], nn.PReLU, 1000), ([196, 32, 16, 6], nn.PReLU, 4099),
+    ([98, 24, 5], nn.ReLU, 777), ([36, 200, 100, 7], nn.ReLU, 130), ([4, 6], nn.PReLU, 5), ([78, 64, 6], nn.PReLU, 1),
+    ([300, 250, 17, 129, 3], nn.PReLU, 515)])
+def test_fused_mlp_matches_the_module(cuda_lib, dims, act, rows):
+    import sus_net_b200 as S
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda")
+    torch.manual_seed(len(dims) * 1000 + rows)
+    m = RefMLP(dims, act).to(dev)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() > 1:
+                p.mul_(2.0)
+    T = 2 if dims[0] % 2 == 0 else 1
+    ns = (torch.rand(rows, T, dims[0] // T, device=dev) < 0.15).float() * torch.randint(1, 9, (rows, T, dims[0] // T), device=dev)
+    sp = torch.zeros(rows, T, 1, device=dev)
+    f = S.FusedMLP(m)
+    got = f(sp, ns)
+    with torch.no_grad():
+        want = m.double()(sp.double(), ns.double()).float()
+        m.float()
+    scale = want.abs().amax(dim=1, keepdim=True).clamp(min=1.0)
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    assert float(((got - want).abs() / scale).max()) < 2e-5
+    # the live parameters are read at every call
+    with torch.no_grad():
+        m.model[0].weight.mul_(0.5)
+        want2 = m(sp, ns)
+    got2 = f(sp, ns)
+    assert float(((got2 - want2).abs() / want2.abs().amax(dim=1, keepdim=True).clamp(min=1.0)).max()) < 2e-5
+    if rows > 1:
+        assert not torch.equal(got, got2)
+
+
+def test_fused_mlp_scope(cuda_lib):
+    import sus_net_b200 as S
+
+    assert S.FusedMLP.supports(RefMLP([8, 4, 2]))
+    assert not S.FusedMLP.supports(nn.Sequential(nn.Linear(4, 4), nn.Tanh(), nn.Linear(4, 2)))
+    assert not S.FusedMLP.supports(nn.Conv2d(1, 1, 1)) and not S.FusedMLP.supports(None)
+    with pytest.raises(NotImplementedError):
+        S.FusedMLP(nn.Sequential(nn.Linear(4, 4), nn.Tanh(), nn.Linear(4, 2)))
+    big = RefMLP([16, 400, 400, 2]).to("cuda")  # two adjacent 400-wide layers: 410 KB of activations per row tile
+    with pytest.raises(NotImplementedError):
+        S.FusedMLP(big)(torch.zeros(4, 1, 1, device="cuda"), torch.zeros(4, 1, 16, device="cuda"))

@@ -7,7 +7,15 @@
 set -x
 OUT=gpurun_out
 BENCH="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline"
+python -c "from sus_net_b200 import build as B; print(B._source_hash())" > $OUT/r02_lib_hash.txt
 $BENCH > $OUT/r02_limiter_plain.json 2> $OUT/r02_limiter_plain.err || exit 1
+if [ "$1" == "--traffic-only" ]; then
+  M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum"
+  ncu --metrics $M --clock-control none -k regex:k_step_ws -s 3 -c 2 --csv --log-file $OUT/r02_limiter_metrics.csv $BENCH > $OUT/r02_limiter_metrics.log 2>&1
+  SUSNET_COMPRESSIBLE=0 ncu --metrics $M --clock-control none -k regex:k_step_ws -s 3 -c 1 --csv --log-file $OUT/r02_limiter_metrics_plainmem.csv $BENCH > $OUT/r02_limiter_metrics_plainmem.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra > $OUT/r02_launches.log 2>&1
+  exit 0
+fi
 ncu --set full --clock-control none --import-source on -k regex:k_step_ws -s 3 -c 1 -f -o $OUT/r02_limiter_full $BENCH > $OUT/r02_limiter_full.log 2>&1
 ncu --query-metrics 2>/dev/null | grep -i -E "compress|ltcfabric|l1tex2xbar|lts__t_sectors_op_write|lts__t_sectors_srcunit_tex_op_write|lts__d_sectors" > $OUT/r02_limiter_metric_names.txt
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__m_l1tex2xbar_write_bytes.sum,l1tex__m_xbar2l1tex_read_bytes.sum"
