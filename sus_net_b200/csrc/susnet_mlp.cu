@@ -36,11 +36,19 @@ struct MlpParams {
 // for the last layer.  CT = columns per thread (column block = 16 * CT); M is processed in blocks of 16 * CT columns.
 template <int CT>
 __device__ __forceinline__ void layer(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ alpha,
-                                      int act, int K, int M, const float* __restrict__ in, float* __restrict__ outs,
-                                      float* __restrict__ gout, int64_t row0, int64_t n_rows, int out_stride, float* wst) {
+                                      int act, int K, int M, int in_off, int out_off,
+                                      float* __restrict__ gout, int64_t row0, int64_t n_rows, int out_stride, int wst_off) {
+  // offsets into the dynamic shared array, NOT generic pointers: with pointers picked from a runtime-indexed table the compiler
+  // emitted generic LD.E.128 for the operand loads of the inner loop instead of LDS.128
+  extern __shared__ __align__(128) float smem[];
+  const float* in = smem + in_off;
+  float* outs = smem + out_off;
+  float* wst = smem + wst_off;
   const int tid = threadIdx.x;
-  const int rg = tid & 15, cg = tid >> 4;  // row group (8 rows), column group (CT columns)
-  const int r0 = rg * 8;
+  const int rg = tid & 15, cg = tid >> 4;  // row group, column group (CT columns)
+  // a thread's 8 rows are r0 .. r0+3 and 64+r0 .. 64+r0+3 with r0 = 4 * rg: the 16 row-group threads of a half-warp read 256
+  // contiguous bytes per LDS.128 (rows 8 * rg .. would put four threads on every bank: measured 22 TFLOP/s)
+  const int r0 = rg * 4;
   constexpr int CB = 16 * CT;  // columns per block
   const float a = (act == SUS_ACT_PRELU && alpha) ? alpha[0] : 0.0f;
   for (int m0 = 0; m0 < M; m0 += CB) {
@@ -82,10 +90,9 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
       const float* w = wst + buf * (kKc * CBP) + cg * CT;
       const float* xin = in + (int64_t)(c * kKc) * kRows + r0;
       const int kmax = K - c * kKc < kKc ? K - c * kKc : kKc;
-#pragma unroll 4
-      for (int kk = 0; kk < kmax; ++kk) {
+      auto kstep = [&](int kk) {
         const float4 x0 = *reinterpret_cast<const float4*>(xin + kk * kRows);
-        const float4 x1 = *reinterpret_cast<const float4*>(xin + kk * kRows + 4);
+        const float4 x1 = *reinterpret_cast<const float4*>(xin + kk * kRows + 64);
         const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
         float wv[CT];
         if (CT >= 4) {
@@ -102,6 +109,12 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < CT; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+      };
+      if (kmax == kKc) {  // full chunk: straight-line code, the loads of the next k-steps overlap the FFMAs
+#pragma unroll
+        for (int kk = 0; kk < kKc; ++kk) kstep(kk);
+      } else {
+        for (int kk = 0; kk < kmax; ++kk) kstep(kk);
       }
       if (c + 1 < n_chunks) put(buf ^ 1);  // (the other buffer was last read before the barrier that ended chunk c - 1)
       __syncthreads();
@@ -122,12 +135,14 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
       }
       if (gout) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (row0 + r0 + i < n_rows) gout[(row0 + r0 + i) * out_stride + m] = v[i];
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = row0 + r0 + (i & 3) + (i >> 2) * 64;
+          if (row < n_rows) gout[row * out_stride + m] = v[i];
+        }
       } else {
         float* o = outs + (int64_t)m * kRows + r0;
         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<float4*>(o + 64) = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
   }
@@ -136,32 +151,46 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
 
 __global__ void __launch_bounds__(kThreads, 1) k_mlp_forward(const __grid_constant__ MlpParams p) {
   extern __shared__ __align__(128) float smem[];
-  float* region[2] = {smem, smem + (size_t)p.region_b_floats * kRows};  // [0]: even positions (input, h2, ...), [1]: odd
-  float* wst = region[1] + (size_t)p.region_a_floats * kRows;          // 2 x kKc x (128 + 4) floats
+  const int region_off[2] = {0, p.region_b_floats * kRows};  // [0]: even positions (input, h2, ...), [1]: odd
+  const int wst_off = region_off[1] + p.region_a_floats * kRows;  // 2 x kKc x (128 + 4) floats
+  float* region[2] = {smem + region_off[0], smem + region_off[1]};
   const SusMlpSpec& s = p.s;
   const int K0 = s.dims[0];
   const int64_t n_tiles = (p.n_rows + kRows - 1) / kRows;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kRows;
-    // input rows -> k-major region 0 (lane = row: conflict-free shared stores; the strided global reads hit each 32-byte
-    // sector K0 / 8 times in a row, the L1 absorbs them)
+    // input rows -> k-major region 0.  The tile's rows are one contiguous block of global memory: copy it with coalesced
+    // 128-bit loads into region 1 (free until layer 0 writes its output there), then transpose shared -> shared (lane = row:
+    // conflict-free stores, 2-way conflicts on the loads).  Strided 4-byte global loads took 15 % of the kernel, more when
+    // the features live in L2-compressible memory.
     {
+      const int64_t n_valid = p.n_rows - row0 < kRows ? p.n_rows - row0 : kRows;
+      const int64_t n_floats = n_valid * K0;
+      const float* src = p.x + row0 * K0;
+      float* raw = region[1];
+      if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const int64_t n4 = n_floats >> 2;
+        for (int64_t i = threadIdx.x; i < n4; i += kThreads) reinterpret_cast<float4*>(raw)[i] = reinterpret_cast<const float4*>(src)[i];
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n_floats; i += kThreads) raw[i] = src[i];
+      } else {
+        for (int64_t i = threadIdx.x; i < n_floats; i += kThreads) raw[i] = src[i];
+      }
+      __syncthreads();
       const int r = threadIdx.x & (kRows - 1), half = threadIdx.x >> 7;
-      const bool ok = row0 + r < p.n_rows;
-      const float* src = p.x + (row0 + r) * K0;
-      for (int k = half; k < K0; k += 2) region[0][(int64_t)k * kRows + r] = ok ? src[k] : 0.0f;
+      const bool ok = r < n_valid;
+      for (int k = half; k < K0; k += 2) region[0][(int64_t)k * kRows + r] = ok ? raw[(int64_t)r * K0 + k] : 0.0f;
     }
     __syncthreads();
     for (int l = 0; l < s.n_layers; ++l) {
       const int K = s.dims[l], M = s.dims[l + 1];
       const bool last = l == s.n_layers - 1;
-      const float* in = region[l & 1];
-      float* outs = region[(l + 1) & 1];
+      const int in = (l & 1) ? region_off[1] : region_off[0];
+      const int outs = (l & 1) ? region_off[0] : region_off[1];
       const int act = last ? SUS_ACT_NONE : s.activation;
       float* gout = last ? p.out : nullptr;
-      if (M > 64) layer<8>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst);
-      else if (M > 16) layer<4>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst);
-      else layer<1>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst);
+      if (M > 64) layer<8>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      else if (M > 16) layer<4>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      else layer<1>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
     }
   }
 }
@@ -180,6 +209,7 @@ extern "C" int sus_mlp_forward(const SusMlpSpec* spec, const float* x, int64_t n
     if (l == spec->n_layers) break;
     if (l & 1) { if (spec->dims[l] > a) a = spec->dims[l]; } else { if (spec->dims[l] > b) b = spec->dims[l]; }
   }
+  if (a < spec->dims[0]) a = spec->dims[0];  // region 1 also stages the raw (row-major) input tile before layer 0 runs
   const size_t smem = ((size_t)(a + b) * kRows + 2 * kKc * 132) * sizeof(float);
   int prev = -1;
   cudaGetDevice(&prev);

@@ -29,7 +29,7 @@ class RefMLP(nn.Module):  # dqn.py:72-93
 @pytest.mark.parametrize("dims,act,rows", [
     ([98, 256, 128, 64, 16, 6], nn.PReLU, 131072), ([98, 256, 128, 64, 16, 6], nn.PReLU, 1000), ([196, 32, 16, 6], nn.PReLU, 4099),
     ([98, 24, 5], nn.ReLU, 777), ([36, 200, 100, 7], nn.ReLU, 130), ([4, 6], nn.PReLU, 5), ([78, 64, 6], nn.PReLU, 1),
-    ([300, 250, 17, 129, 3], nn.PReLU, 515)])
+    ([200, 150, 17, 129, 3], nn.PReLU, 515)])
 def test_fused_mlp_matches_the_module(cuda_lib, dims, act, rows):
     import sus_net_b200 as S
 

@@ -25,11 +25,12 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--kernels", action="store_true")
+    ap.add_argument("--torch-mlp", action="store_true", help="evaluate the Q-network with the torch module instead of sus_mlp_forward")
     a = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = a.tf32
     dev = torch.device("cuda", 0)
     N = a.envs
-    env, loop = build(N, dev, 0, a.batch, graphs=False)
+    env, loop = build(N, dev, 0, a.batch, graphs=False, fused_mlp=not a.torch_mlp)
     loop.run(10)
     actor, buf, feat, seq = loop.actor, loop.buf, loop.feat, loop.seq
     names = ("q_network_forward", "select_actions_kernel", "fused_step_encode_kernel", "export_flat+replay_push", "sample_batch", "train_step")
@@ -46,8 +47,8 @@ def main():
         loop.eps.fill_(0.3)
         sp, ns = seq.views()
         e0 = ev()
-        with torch.no_grad():
-            q = loop.imposter_model(torch.zeros(N, 1, 1, device=dev), ns[0]).float().contiguous()
+        with torch.no_grad():  # the network the actor evaluates: the one-launch MLP kernel (or the torch module with --torch-mlp)
+            q = loop.actor._infer["imp"](torch.zeros(N, 1, 1, device=dev), ns[0]).float().contiguous()
         e1 = ev()
         # (act_kernel would run the network again; call the selection kernel directly on the Q-values just computed)
         import ctypes as C
@@ -93,7 +94,7 @@ def main():
     # the same loop through BatchedTrainingLoop, eager and as CUDA graphs: wall time per iteration
     totals = {}
     for graphs in (False, True):
-        env2, loop2 = build(N, dev, 0, a.batch, graphs=graphs)
+        env2, loop2 = build(N, dev, 0, a.batch, graphs=graphs, fused_mlp=not a.torch_mlp)
         loop2.run(40)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
@@ -102,6 +103,7 @@ def main():
         totals["cuda_graphs" if graphs else "eager"] = 1e3 * (time.perf_counter() - t0) / a.iters
         del env2, loop2
     print(json.dumps({"envs": N, "iters": a.iters, "batch": a.batch, "tf32_q_network": a.tf32,
+                      "q_network": "torch module" if a.torch_mlp else "sus_mlp_forward (one launch, fp32 FFMA)",
                       "device_ms_per_iteration_by_phase (eager, CUDA events; train phases amortised over 5 iterations)": per_iter,
                       "sum_of_phases_ms": sum(per_iter.values()), "library_kernel_launches_per_iteration": launches,
                       "wall_ms_per_iteration": totals,

@@ -44,7 +44,7 @@ class MLPQ(nn.Module):
         return m
 
 
-def build(N, dev, rank, batch, graphs, iters_for_schedule=2000):
+def build(N, dev, rank, batch, graphs, iters_for_schedule=2000, fused_mlp=True):
     env = S.BatchedImposterTrainingGround(n_crew=4, n_jobs=0, time_step_reward=0, kill_reward=-3, sabotage_reward=0,
                                           end_of_game_reward=0, num_envs=N, seed=7, env_id_base=rank * N, device=dev)
     feat = S.FlatFeaturizer(env, S.CompositeFeaturizer([S.OneHotAgentPositionFeaturizer(env), S.AliveCrewFeaturizer(env),
@@ -56,7 +56,7 @@ def build(N, dev, rank, batch, graphs, iters_for_schedule=2000):
     sched = S.ExponentialSchedule(1.0, 0.05, iters_for_schedule)
     # crew_model=None: the reference's RandomEquiprobable crew (uniform over the crew's role list)
     loop = S.BatchedTrainingLoop(env, buf, feat, imp, None, trainer, sched, batch_size=batch, train_step_interval=5,
-                                 target_update_interval=1000, use_graphs=graphs)
+                                 target_update_interval=1000, use_graphs=graphs, fused_mlp=fused_mlp)
     return env, loop
 
 
@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core GEMMs in the Q-network")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--torch-mlp", action="store_true", help="evaluate the acting Q-network with the torch module instead of sus_mlp_forward")
     a = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = a.tf32
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
@@ -75,7 +76,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N = a.envs_per_gpu
-    env, loop = build(N, dev, rank, a.batch, not a.no_graphs)
+    env, loop = build(N, dev, rank, a.batch, not a.no_graphs, fused_mlp=not a.torch_mlp)
     loop.run(40)  # warm-up: eager iterations, graph captures, first replays
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -100,7 +101,8 @@ def main():
         print(json.dumps({"config": "cfg5 batched DQN loop (imposter MLP on fused Flat-98 features -> selection kernel -> fused step "
                                     "+ encode -> replay push; train step every 5 iterations)",
                           "n_gpus": world, "envs_per_gpu": N, "global_envs": world * N, "iterations": iters, "wall_s": dt,
-                          "cuda_graphs": not a.no_graphs, "tf32_q_network": a.tf32, "batch_size": a.batch,
+                          "cuda_graphs": not a.no_graphs, "tf32_q_network": a.tf32,
+                          "acting_q_network": "torch module" if a.torch_mlp else "sus_mlp_forward (one launch, fp32 FFMA)", "batch_size": a.batch,
                           "ms_per_iteration": 1e3 * dt / iters,
                           "env_steps_per_s_in_training_loop": world * N * iters / dt,
                           "train_steps": len(losses), "last_losses": losses[-1],
