@@ -201,6 +201,16 @@ int sus_compact_layout(const SusConfig *cfg, SusCompactLayout *out /*host*/);
  * (NaN for codes >= n_codes); A * (invalid_code + 1) doubles.  Host call, no GPU work. */
 int sus_reward_lut(const SusConfig *cfg, double *out /*host*/);
 
+/* HOST helpers of the compact protocol (plain CPU code over host pointers, `threads` <= 0: pick; no GPU work).
+ * sus_host_pack_actions: [N][A] role-list indices (SUS_U8 / SUS_I32 / SUS_I64) -> [N][action_bytes] records; an index that does
+ * not fit its field becomes the field's maximum, which the kernel then rejects like any index outside the role list.
+ * sus_host_decode_results: [N][result_bytes] records -> what step() returns per env (base.py:397-407): rewards [N][A] float32 or
+ * float64 through the table of sus_reward_lut (NaN for a rejected env), done [N], truncated [N]; NULL outputs are skipped. */
+int sus_host_pack_actions(const SusConfig *cfg, const void *actions /*host*/, int32_t dtype, int64_t n_envs,
+                          uint8_t *packed /*host*/, int32_t threads);
+int sus_host_decode_results(const SusConfig *cfg, const uint8_t *records /*host*/, int64_t n_envs, void *rewards /*host*/,
+                            int32_t rewards_dtype, uint8_t *done /*host*/, uint8_t *truncated /*host*/, int32_t threads);
+
 /* FourRoomEnv.__init__ & co. (base.py:103-228): validates like _validate_init_args (base.py:243-249,
  * pred_prey.py:75-76), builds the wall grid, allocates the structure-of-arrays state for num_envs envs on
  * `device`.  The envs are NOT reset. */

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsusnet_b200.so")
-SOURCES = ["susnet_api.cu", "susnet_replay.cu", "susnet_alloc.cu", "susnet_policy.cu", "susnet_mlp.cu"]
+SOURCES = ["susnet_api.cu", "susnet_replay.cu", "susnet_alloc.cu", "susnet_policy.cu", "susnet_mlp.cu", "susnet_host.cu"]
 HEADERS = ["susnet_device.cuh", "susnet_encode.cuh", "susnet_tile.cuh", "susnet_ws.cuh", os.path.join("..", "..", "include", "susnet_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",

@@ -24,6 +24,7 @@ from . import _lib as L
 
 class CompactProtocol:
     def __init__(self, env):
+        self._lib, self._cfg = env.lib, env._cfg
         self.n_agents = A = env.n_agents
         lay = L.SusCompactLayout()
         L.check(env.lib.sus_compact_layout(C.byref(env._cfg), C.byref(lay)))
@@ -43,7 +44,14 @@ class CompactProtocol:
             for i in range(self.n_agents):
                 rec |= a[:, i] << (i * self.action_bits)
             return torch.stack([(rec >> (8 * b)) & 0xFF for b in range(self.action_bytes)], dim=1).to(torch.uint8)
-        a = np.asarray(actions).astype(np.uint64)
+        a = np.ascontiguousarray(actions)
+        if a.dtype in (np.uint8, np.int32, np.int64) and a.ndim == 2:  # the library's host packer (threads over N)
+            out = np.empty((a.shape[0], self.action_bytes), dtype=np.uint8)
+            dt = {np.dtype(np.uint8): L.U8, np.dtype(np.int32): L.I32, np.dtype(np.int64): L.I64}[a.dtype]
+            L.check(self._lib.sus_host_pack_actions(C.byref(self._cfg), a.ctypes.data_as(C.c_void_p), dt, a.shape[0],
+                                                    out.ctypes.data_as(C.c_void_p), 0))
+            return out
+        a = a.astype(np.uint64)
         rec = np.zeros(a.shape[0], dtype=np.uint64)
         for i in range(self.n_agents):
             rec |= a[:, i] << np.uint64(i * self.action_bits)
@@ -73,6 +81,22 @@ class CompactProtocol:
 
     def decode(self, results, dtype=np.float64):
         """(N, result_bytes) uint8 records -> (rewards (N, A) `dtype`, dones (N,) bool, truncated (N,) bool)."""
+        if isinstance(results, torch.Tensor):
+            results = results.detach().cpu().numpy()
+        results = np.ascontiguousarray(results, dtype=np.uint8)
+        if np.dtype(dtype) in (np.dtype(np.float32), np.dtype(np.float64)):  # the library's host decoder (threads over N)
+            n = results.shape[0]
+            rewards = np.empty((n, self.n_agents), dtype=dtype)
+            done, trunc = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+            L.check(self._lib.sus_host_decode_results(
+                C.byref(self._cfg), results.ctypes.data_as(C.c_void_p), n, rewards.ctypes.data_as(C.c_void_p),
+                L.F32 if np.dtype(dtype) == np.dtype(np.float32) else L.F64, done.ctypes.data_as(C.c_void_p),
+                trunc.ctypes.data_as(C.c_void_p), 0))
+            return rewards, done.view(bool), trunc.view(bool)
+        return self.decode_numpy(results, dtype)
+
+    def decode_numpy(self, results, dtype=np.float64):
+        """The same decode in numpy (the written spec of the record format; tests compare both)."""
         rec = self._records(results)
         A, rb = self.n_agents, self.reward_bits
         m = np.uint64((1 << rb) - 1)

@@ -227,3 +227,43 @@ def test_missing_cuda_library_is_an_import_error(lib, monkeypatch, tmp_path):
     src = "".join(open(os.path.join(ROOT, "sus_net_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "sus_net_b200"))
                   if f.endswith(".py"))
     assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_compact_protocol_host_codec_matches_the_numpy_spec(lib):
+    """sus_host_pack_actions / sus_host_decode_results (threaded C over host buffers) against the numpy statement of the record
+    format in sus_net_b200/compact.py, for every variant's geometry, ragged sizes, both reward dtypes, and out-of-field indices."""
+    from sus_net_b200.compact import CompactProtocol
+
+    L = lib.lib()
+
+    class Env:  # the three attributes CompactProtocol reads
+        pass
+
+    rng = np.random.default_rng(0)
+    for kw in (dict(), dict(variant=1, n_crew=2), dict(variant=1, n_imposters=3, n_crew=5, n_jobs=2), dict(variant=2, n_crew=1, n_jobs=0)):
+        e = Env()
+        e.lib, e._cfg = L, cfg(lib, kill_reward=-5.1, complete_job_reward=1 / 3, sabotage_reward=3.0, game_end_reward=10.0,
+                               dead_penalty=-2.0, vote_reward=0.7, time_step_reward=-0.5, **kw)
+        e.n_agents = e._cfg.n_imposters + e._cfg.n_crew
+        cp = CompactProtocol(e)
+        for n in (0, 1, 7, 70001):
+            a = rng.integers(0, 1 << cp.action_bits, (n, e.n_agents))
+            for dt in (np.uint8, np.int32, np.int64):
+                p = cp.pack_actions(a.astype(dt))
+                assert p.shape == (n, cp.action_bytes) and np.array_equal(cp.unpack_actions(p), a)
+            if n:
+                bad = a.astype(np.int64).copy()
+                bad[0, 0] = -3; bad[n - 1, e.n_agents - 1] = 1 << 20
+                q = cp.unpack_actions(cp.pack_actions(bad))
+                assert q[0, 0] == (1 << cp.action_bits) - 1 and q[n - 1, e.n_agents - 1] == (1 << cp.action_bits) - 1
+            codes = rng.integers(0, cp.invalid_code + 1, (n, e.n_agents)).astype(np.uint64)
+            rec = np.zeros(n, dtype=np.uint64)
+            for i in range(e.n_agents):
+                rec |= codes[:, i] << np.uint64(i * cp.reward_bits)
+            rec |= rng.integers(0, 4, n).astype(np.uint64) << np.uint64(e.n_agents * cp.reward_bits)
+            r = np.stack([(rec >> np.uint64(8 * b)) & np.uint64(255) for b in range(cp.result_bytes)], 1).astype(np.uint8).reshape(n, cp.result_bytes)
+            want = cp.decode_numpy(r)
+            got = cp.decode(r)
+            assert np.array_equal(got[0].view(np.int64), want[0].view(np.int64)) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+            got32 = cp.decode(r, np.float32)
+            assert np.array_equal(got32[0].view(np.int32), want[0].astype(np.float32).view(np.int32))
