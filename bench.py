@@ -458,6 +458,60 @@ def other_configs(S, dev, rank, K, peak):
     out["cfg2_itg_1v1_wall_4096_envs_step_only"] = {"envs": n, "kernel_ms": k_ms, "env_steps_per_s_with_sampler": n / (step_ms * 1e-3),
                                                    "rollout_env_steps_per_s": n * 1000 / (t0.elapsed_time(t1) * 1e-3)}
     del env
+    out["small_kernels"] = small_kernels(S, dev, K, peak)
+    return out
+
+
+def small_kernels(S, dev, K, peak):
+    """The path's two small kernels with their own byte counts (cfg4, 1 Mi envs): K3 `k_sample_actions` (reads the 16-byte aux
+    record, writes A int32 actions: 36 B per env) and row f1's `k_replay_push` (T = 1: reads the sequence row, next_flat,
+    cur_flat, actions, rewards, flags, imposters; writes states, next_states, the next sequence row, int64 actions, rewards,
+    done, imposters: 24 S + 20 A + 7 = 827 B per transition at S = 30, A = 5)."""
+    import ctypes as C
+
+    import torch
+
+    from sus_net_b200 import _lib as L
+
+    N = 1 << 20
+    env = S.BatchedFourRoomEnv(1, 4, 5, num_envs=N, seed=1234, device=dev)
+    env.reset()
+    buf = S.ReplayBuffer(2 * N, env.flattened_state_size, 1, env.n_agents, 1, device=dev)
+    buf.attach(env)
+    for _ in range(3):
+        buf.collect_step(env.sample_actions())
+    torch.cuda.synchronize(dev)
+    ev_s, ev_p = [], []
+    for _ in range(K):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(); acts = env.sample_actions(); a1.record()
+        ev_s.append((a0, a1))
+        next_flat, rewards, dones, truncated, _ = env.step(acts)
+        env.flat_states(out=buf._cur_flat)
+        p = L.SusReplayPush(N=N, M=buf.max_size, idx=buf.idx, T=1, S=buf.state_size, A=buf.n_agents, n_imposters=1,
+                            seq_in=buf._seq[0].data_ptr(), seq_out=buf._seq[1].data_ptr(), next_flat=next_flat.data_ptr(),
+                            cur_flat=buf._cur_flat.data_ptr(), actions=acts.data_ptr(), actions_dtype=L.I32,
+                            rewards=rewards.data_ptr(), done=dones.data_ptr(), truncated=truncated.data_ptr(),
+                            imposters=env._imposters_buf.data_ptr(), states=buf.states.data_ptr(), r_actions=buf.actions.data_ptr(),
+                            r_rewards=buf.rewards.data_ptr(), next_states=buf.next_states.data_ptr(), r_dones=buf.dones.data_ptr(),
+                            r_imposters=buf.imposters.data_ptr())
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(); L.check(env.lib.sus_replay_push(C.byref(p), dev.index, env._stream())); p1.record()
+        ev_p.append((p0, p1))
+        buf._seq.reverse()
+        buf.idx = (buf.idx + N) % buf.max_size
+    torch.cuda.synchronize(dev)
+    med = lambda evs: sorted(s.elapsed_time(e) for s, e in evs)[len(evs) // 2]  # noqa: E731
+    ms_s, ms_p = med(ev_s), med(ev_p)
+    S_, A_ = env.flattened_state_size, env.n_agents
+    b_push = (3 * S_ * 4) + (A_ * 4) + (A_ * 4) + 2 + 2 + (3 * S_ * 4) + (A_ * 8) + (A_ * 4) + 1 + 2
+    out = {"k_sample_actions": {"envs": N, "kernel_ms": ms_s, "algorithmic_bytes_per_env": 16 + 4 * A_,
+                                "achieved_gbs": (16 + 4 * A_) * N / (ms_s * 1e-3) / 1e9},
+           "k_replay_push": {"transitions": N, "kernel_ms": ms_p, "algorithmic_bytes_per_transition": b_push,
+                             "achieved_gbs": b_push * N / (ms_p * 1e-3) / 1e9}}
+    for v in out.values():
+        v["frac_of_hbm_copy_peak"] = v["achieved_gbs"] / peak
+    del env, buf
     return out
 
 

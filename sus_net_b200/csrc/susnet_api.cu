@@ -1384,7 +1384,8 @@ int device_info(int device, DeviceInfo& d) {
   return SUS_OK;
 }
 
-// SUSNET_PATH=direct forces the register/LSU store path, SUSNET_PATH=tma (default) the shared-memory + TMA path.
+// false only for SUSNET_PATH=direct (register / LSU stores everywhere).  Which staged path runs is decided by want_ws() /
+// want_staged_flat() below: unset -> warp-specialised emitter for Global / Perspective, byte-staged rows for Flat.
 bool want_tma() {
   const char* v = std::getenv("SUSNET_PATH");
   return !(v && std::strcmp(v, "direct") == 0);

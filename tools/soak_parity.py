@@ -28,13 +28,15 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 20)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--check-every", type=int, default=100)
-    ap.add_argument("--config", choices=["global", "flat", "tagging"], default="global")
+    ap.add_argument("--config", choices=["global", "flat", "tagging", "compact"], default="global")
     a = ap.parse_args()
     N, T = a.envs, a.steps
     if a.config == "flat":
         return soak_flat(N, T, a.check_every)
     if a.config == "tagging":
         return soak_tagging(N, T, a.check_every)
+    if a.config == "compact":
+        return soak_compact(N, T, a.check_every)
     cfg = oracle.default_config("base", n_crew=4, n_jobs=5)
     env = S.BatchedFourRoomEnv(1, 4, 5, num_envs=N, seed=99, device="cuda:0")
     feat = S.GlobalFeaturizer(env)
@@ -131,6 +133,48 @@ def soak_tagging(N, T, check_every):
     print(json.dumps({"config": "cfg3 FourRoomEnvWithTagging 1v2, 5 jobs, step only (sample_actions + step)", "envs": N, "steps": T,
                       "env_steps": N * T, "full_state_comparisons": checks, "finished_trajectories": stats["episodes"],
                       "stats": stats, "wall_s": round(time.time() - t0, 1), "result": "identical"}))
+
+
+def soak_compact(N, T, check_every):
+    """The headline config through the COMPACT HOST PROTOCOL at full size: bit-packed actions in, reward codes + done / truncated
+    bits out of the fused step + Global encode; at every checkpoint the records of all envs are decoded on the host (threaded C
+    decoder AND its numpy statement) and the float64 rewards must equal the oracle's BIT PATTERNS, with flags, states and stats."""
+    cfg = oracle.default_config("base", n_crew=4, n_jobs=5)
+    env = S.BatchedFourRoomEnv(1, 4, 5, num_envs=N, seed=99, device="cuda:0")
+    env.emit_next_states = False
+    feat = S.GlobalFeaturizer(env)
+    cp = env.compact
+    orc = oracle.OracleEnv(cfg, N, seed=99)
+    oracle.set_threads(os.cpu_count() or 1)
+    assert np.array_equal(env.reset()[0].cpu().numpy().astype(np.int64), orc.reset())
+    rec = torch.empty((N, cp.result_bytes), dtype=torch.uint8, device=env.device)
+    t0, out, checks, oa = time.time(), None, 0, None
+    for t in range(1, T + 1):
+        acts = env.sample_actions()
+        env.step(cp.pack_actions(acts).contiguous(), featurizer=feat, packed_actions=True, packed_out=rec)
+        oa = orc.sample_actions(out=oa)
+        out = orc.step(oa, want_flat=False, want_metrics=False, out=out)
+        if t % check_every == 0 or t == T:
+            h = rec.cpu().numpy()
+            r, d, tr = cp.decode(h)
+            r2, d2, tr2 = cp.decode_numpy(h)
+            assert np.array_equal(r.view(np.int64), out["rewards"].view(np.int64)), f"decoded rewards differ at step {t}"
+            assert np.array_equal(r2.view(np.int64), r.view(np.int64)) and np.array_equal(d, d2) and np.array_equal(tr, tr2)
+            assert np.array_equal(d, out["done"] != 0) and np.array_equal(tr, out["trunc"] != 0), f"flags differ at step {t}"
+            assert np.array_equal(acts.cpu().numpy(), oa), f"sampled actions differ at step {t}"
+            assert np.array_equal(env.flat_states(torch.int64).cpu().numpy(), orc.flat_states()), f"states differ at step {t}"
+            assert np.array_equal(env.episode_stats().cpu().numpy(), orc.stats()), f"episode stats differ at step {t}"
+            checks += 1
+    env.check_actions()
+    cur = orc.flat_states()
+    views = feat.generate_featurized_states()
+    k = min(N, 65536)
+    want_sp, want_ns = oracle.encode_global(cfg, cur[:k])
+    assert np.array_equal(views[0][0].detach()[:k, 0].cpu().numpy(), want_sp) and np.array_equal(views[4][1].detach()[:k, 0].cpu().numpy(), want_ns[4])
+    stats = dict(zip(S.STAT_KEYS, [int(x) for x in orc.stats()]))
+    print(json.dumps({"config": "cfg4 FourRoomEnv 1v4 + Global encode through the compact host protocol (packed actions in, reward codes out)",
+                      "envs": N, "steps": T, "env_steps": N * T, "full_comparisons": checks, "record_bytes": [cp.action_bytes, cp.result_bytes],
+                      "finished_trajectories": stats["episodes"], "stats": stats, "wall_s": round(time.time() - t0, 1), "result": "identical"}))
 
 
 if __name__ == "__main__":
