@@ -650,7 +650,12 @@ def run_b200_arm(args):
     del a
     stats_local = env.episode_stats()
     del env
-    other = other_configs(S, dev, rank, K, peak) if world == 1 and not args.no_extra else None
+    other = None
+    if world == 1 and not args.no_extra:
+        try:  # extras must never cost the headline line
+            other = other_configs(S, dev, rank, K, peak)
+        except Exception as exc:  # noqa: BLE001
+            other = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- arm 2: end to end through the public API with host buffers
     e2e = None
@@ -760,7 +765,11 @@ def run_b200_arm(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
-            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            except Exception as exc:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "",
+                                        "error": f"{type(exc).__name__}: {exc}"[:300]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -293,6 +293,13 @@ class _FlatAdam:
         self.step = torch.zeros((), device=dev, dtype=torch.float64)
         self.lr, (self.b1, self.b2), self.eps = float(g["lr"]), g["betas"], float(g["eps"])
 
+    def state_dict(self):
+        """Moments and step count (the wrapped torch optimizer's own state stays empty: its `step()` is never called)."""
+        return {"m": self.m.clone(), "v": self.v.clone(), "step": self.step.clone(), "lr": self.lr, "betas": (self.b1, self.b2), "eps": self.eps}
+
+    def load_state_dict(self, sd):
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step.copy_(sd["step"])
+
     def begin_train_step(self):
         self.acc.zero_()
 
@@ -344,6 +351,16 @@ class DQNTeamTrainer:
         if id(opt) not in self._adam:
             self._adam[id(opt)] = _FlatAdam(opt)
         return self._adam[id(opt)]
+
+    def optimizer_state_dict(self):
+        """{"imposter": ..., "crew": ...}: Adam moments / step counts of the device-gated optimizer steps, for checkpoints."""
+        return {name: self._flat(opt).state_dict() for name, opt in (("imposter", self.imposter_optimizer), ("crew", self.crew_optimizer))
+                if opt is not None}
+
+    def load_optimizer_state_dict(self, sd):
+        for name, opt in (("imposter", self.imposter_optimizer), ("crew", self.crew_optimizer)):
+            if opt is not None and name in sd:
+                self._flat(opt).load_state_dict(sd[name])
 
     def train_step(self, batch, featurizer, imposter_model, imposter_target_model, crew_model, crew_target_model):
         dev = batch.states.device

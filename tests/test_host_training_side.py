@@ -245,3 +245,34 @@ def test_flat_adam_two_ranks_gloo_weights_samples_evenly(S):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_trainer_optimizer_state_roundtrip(S):
+    """The device-gated Adam keeps its own moments: they travel through optimizer_state_dict() / load_optimizer_state_dict()."""
+    from sus_net_b200.train import _FlatAdam
+
+    torch.manual_seed(1)
+    m1, m2 = torch.nn.Linear(5, 3), torch.nn.Linear(5, 3)
+    m2.load_state_dict(m1.state_dict())
+    t1 = S.DQNTeamTrainer(torch.optim.Adam(m1.parameters(), lr=1e-2), None, 0.9)
+    t2 = S.DQNTeamTrainer(torch.optim.Adam(m2.parameters(), lr=1e-2), None, 0.9)
+    x, y = torch.randn(7, 5), torch.randn(7, 3)
+
+    def step(tr, model):
+        fa = tr._flat(tr.imposter_optimizer)
+        fa.begin_train_step(); fa.begin_view()
+        sq = ((model(x) - y) ** 2).sum()
+        sq.backward()
+        fa.apply(torch.tensor(7.0), sq.detach())
+
+    for _ in range(3):
+        step(t1, m1)
+    sd = t1.optimizer_state_dict()
+    assert set(sd) == {"imposter"} and float(sd["imposter"]["step"]) == 3.0
+    with torch.no_grad():
+        for p, q in zip(m2.parameters(), m1.parameters()):
+            p.copy_(q)
+    t2._flat(t2.imposter_optimizer)  # flatten first, then restore
+    t2.load_optimizer_state_dict(sd)
+    step(t1, m1); step(t2, m2)
+    assert all(torch.equal(p, q) for p, q in zip(m1.parameters(), m2.parameters()))
