@@ -163,6 +163,14 @@ class ReferencePool:
         self.pool.join()
 
 
+def host_cores():
+    """Cores this process may run on (torchrun / cgroup affinity respected), not just the machine's count."""
+    try:
+        return len(os.sched_getaffinity(0)) or (os.cpu_count() or 1)
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def reference_available():
     from oracle import ref_harness as H
 
@@ -170,7 +178,7 @@ def reference_available():
 
 
 def port_baseline(target_seconds):
-    threads = os.cpu_count() or 1
+    threads = host_cores()
     n_envs = 65536
     loop = OracleLoop(n_envs, threads)
     rate, _ = loop.rate(3)  # calibration
@@ -204,7 +212,7 @@ def cpu_baseline(target_seconds):
 
 def reference_sample(target_seconds):
     """`bench.py --reference-sample S`: ~S seconds of the unmodified reference loop on every host core -> one JSON line."""
-    procs = os.cpu_count() or 1
+    procs = host_cores()
     pool = ReferencePool(procs)
     try:
         pool.step(20)            # imports, first-call costs
@@ -232,7 +240,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_cores()
     total_steps = args.steps + args.warmup
     budget = 75.0  # seconds for the whole --steps K --warmup W run
     if reference_available():
