@@ -11,6 +11,8 @@
 // 128-wide column blocks), i.e. 4 LDS.128 per 64 FFMA in the inner loop.  fp32 FFMA only: no tensor cores (the north star
 // excludes them), same arithmetic as the reference's CPU float32 forward up to summation order.
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "../../include/susnet_b200.h"
@@ -20,9 +22,11 @@ extern "C" void sus_internal_count_launch(void);
 
 namespace {
 
-constexpr int kRows = 128;     // rows per CTA tile
-constexpr int kThreads = 256;  // 16 row groups x 16 column groups
-constexpr int kKc = 16;        // k per weight chunk
+// Two tile geometries (template parameter ROWS = rows per CTA tile; 2 * ROWS threads = ROWS / 8 row groups x 16 column groups):
+//   128 rows, 256 threads, ONE CTA per SM (213 KB of shared memory at cfg5);
+//    64 rows, 128 threads, TWO CTAs per SM (2 x 112.5 KB): the same eight warps per SM, but while one CTA stages its input tile,
+//    waits at a chunk barrier or runs the narrow tail layers the other one keeps the FFMA pipe busy (SUSNET_MLP_ROWS=64).
+constexpr int kKc = 16;  // k per weight chunk
 
 struct MlpParams {
   SusMlpSpec s;
@@ -34,7 +38,7 @@ struct MlpParams {
 
 // One layer on the CTA's row tile: out[m][r] = act(bias[m] + sum_k W[m][k] * in[k][r]) for m < M, or straight to global memory
 // for the last layer.  CT = columns per thread (column block = 16 * CT); M is processed in blocks of 16 * CT columns.
-template <int CT>
+template <int ROWS, int CT>
 __device__ __forceinline__ void layer(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ alpha,
                                       int act, int K, int M, int in_off, int out_off,
                                       float* __restrict__ gout, int64_t row0, int64_t n_rows, int out_stride, int wst_off) {
@@ -45,8 +49,9 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
   float* outs = smem + out_off;
   float* wst = smem + wst_off;
   const int tid = threadIdx.x;
-  const int rg = tid & 15, cg = tid >> 4;  // row group, column group (CT columns)
-  // a thread's 8 rows are r0 .. r0+3 and 64+r0 .. 64+r0+3 with r0 = 4 * rg: the 16 row-group threads of a half-warp read 256
+  constexpr int kRows = ROWS, kThreads = 2 * ROWS, RG = ROWS / 8, HALF = ROWS / 2;
+  const int rg = tid % RG, cg = tid / RG;  // row group, column group (CT columns)
+  // a thread's 8 rows are r0 .. r0+3 and HALF+r0 .. HALF+r0+3 with r0 = 4 * rg: the row-group threads of a (half-)warp read
   // contiguous bytes per LDS.128 (rows 8 * rg .. would put four threads on every bank: measured 22 TFLOP/s)
   const int r0 = rg * 4;
   constexpr int CB = 16 * CT;  // columns per block
@@ -92,7 +97,7 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
       const int kmax = K - c * kKc < kKc ? K - c * kKc : kKc;
       auto kstep = [&](int kk) {
         const float4 x0 = *reinterpret_cast<const float4*>(xin + kk * kRows);
-        const float4 x1 = *reinterpret_cast<const float4*>(xin + kk * kRows + 64);
+        const float4 x1 = *reinterpret_cast<const float4*>(xin + kk * kRows + HALF);
         const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
         float wv[CT];
         if (CT >= 4) {
@@ -136,21 +141,23 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
       if (gout) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int64_t row = row0 + r0 + (i & 3) + (i >> 2) * 64;
+          const int64_t row = row0 + r0 + (i & 3) + (i >> 2) * HALF;
           if (row < n_rows) gout[row * out_stride + m] = v[i];
         }
       } else {
         float* o = outs + (int64_t)m * kRows + r0;
         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 64) = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<float4*>(o + HALF) = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_mlp_forward(const __grid_constant__ MlpParams p) {
+template <int ROWS>
+__global__ void __launch_bounds__(2 * ROWS, ROWS == 64 ? 2 : 1) k_mlp_forward(const __grid_constant__ MlpParams p) {
   extern __shared__ __align__(128) float smem[];
+  constexpr int kRows = ROWS, kThreads = 2 * ROWS;
   const int region_off[2] = {0, p.region_b_floats * kRows};  // [0]: even positions (input, h2, ...), [1]: odd
   const int wst_off = region_off[1] + p.region_a_floats * kRows;  // 2 x kKc x (128 + 4) floats
   float* region[2] = {smem + region_off[0], smem + region_off[1]};
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_forward(const __grid_consta
         for (int64_t i = threadIdx.x; i < n_floats; i += kThreads) raw[i] = src[i];
       }
       __syncthreads();
-      const int r = threadIdx.x & (kRows - 1), half = threadIdx.x >> 7;
+      const int r = threadIdx.x % kRows, half = threadIdx.x / kRows;
       const bool ok = r < n_valid;
       for (int k = half; k < K0; k += 2) region[0][(int64_t)k * kRows + r] = ok ? raw[(int64_t)r * K0 + k] : 0.0f;
     }
@@ -188,9 +195,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_forward(const __grid_consta
       const int outs = (l & 1) ? region_off[0] : region_off[1];
       const int act = last ? SUS_ACT_NONE : s.activation;
       float* gout = last ? p.out : nullptr;
-      if (M > 64) layer<8>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
-      else if (M > 16) layer<4>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
-      else layer<1>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      if (M > 64) layer<ROWS, 8>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      else if (M > 16) layer<ROWS, 4>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      else layer<ROWS, 1>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
     }
   }
 }
@@ -210,26 +217,54 @@ extern "C" int sus_mlp_forward(const SusMlpSpec* spec, const float* x, int64_t n
     if (l & 1) { if (spec->dims[l] > a) a = spec->dims[l]; } else { if (spec->dims[l] > b) b = spec->dims[l]; }
   }
   if (a < spec->dims[0]) a = spec->dims[0];  // region 1 also stages the raw (row-major) input tile before layer 0 runs
-  const size_t smem = ((size_t)(a + b) * kRows + 2 * kKc * 132) * sizeof(float);
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != device) cudaSetDevice(device);
   int max_smem = 0, sms = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  auto smem_of = [&](int rows) { return ((size_t)(a + b) * rows + 2 * kKc * 132) * sizeof(float); };
+  const char* rows_env = getenv("SUSNET_MLP_ROWS");  // read per call: tests and tools switch geometries inside one process
+  // 128-row tiles unless asked for 64-row tiles, or unless only a 64-row tile of the two widest adjacent layers fits
+  const int rows = ((rows_env && atoi(rows_env) == 64) || smem_of(128) > (size_t)max_smem) ? 64 : 128;
+  const size_t smem = smem_of(rows);
   int rc = SUS_OK;
   if (smem > (size_t)max_smem) {
     rc = sus_internal_fail(SUS_ERR_UNSUPPORTED, "mlp_forward: the two widest adjacent layers do not fit in shared memory (run the module itself)");
   } else if (n_rows > 0) {
-    static size_t granted[64] = {};
-    if (device >= 0 && device < 64 && granted[device] < smem) {
-      cudaFuncSetAttribute(k_mlp_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      granted[device] = smem;
+    static size_t granted[2][64] = {};
+    const int v = rows == 64;
+    if (device >= 0 && device < 64 && granted[v][device] < smem) {
+      if (v) {
+        cudaFuncSetAttribute(k_mlp_forward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_mlp_forward<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      } else {
+        cudaFuncSetAttribute(k_mlp_forward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      }
+      granted[v][device] = smem;
     }
     MlpParams p;
     p.s = *spec; p.x = x; p.out = out; p.n_rows = n_rows; p.region_a_floats = a; p.region_b_floats = b;
-    const int64_t tiles = (n_rows + kRows - 1) / kRows;
-    k_mlp_forward<<<(unsigned)(tiles < sms ? tiles : sms), kThreads, smem, (cudaStream_t)stream>>>(p);
+    const int64_t tiles = (n_rows + rows - 1) / rows;
+    if (v) {
+      // CTAs per SM: 2 when two tiles' activations fit on an SM (cfg5: 2 x 112.5 KB); queried once per (device, size)
+      static size_t occ_smem[64] = {};
+      static int occ_ctas[64] = {};
+      int per_sm = 1;
+      if (device >= 0 && device < 64 && occ_smem[device] == smem) {
+        per_sm = occ_ctas[device];
+      } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mlp_forward<64>, 128, smem);
+        if (per_sm < 1) per_sm = 1;
+        if (device >= 0 && device < 64) { occ_smem[device] = smem; occ_ctas[device] = per_sm; }
+      }
+      static const bool verbose = getenv("SUSNET_MLP_VERBOSE") != nullptr;
+      if (verbose) fprintf(stderr, "sus_mlp_forward: 64-row tiles, %zu bytes of shared memory, %d CTAs per SM\n", smem, per_sm);
+      const int64_t grid = (int64_t)sms * per_sm;
+      k_mlp_forward<64><<<(unsigned)(tiles < grid ? tiles : grid), 128, smem, (cudaStream_t)stream>>>(p);
+    } else {
+      k_mlp_forward<128><<<(unsigned)(tiles < sms ? tiles : sms), 256, smem, (cudaStream_t)stream>>>(p);
+    }
     sus_internal_count_launch();
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) rc = sus_internal_fail(SUS_ERR_CUDA, cudaGetErrorString(err));

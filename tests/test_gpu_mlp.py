@@ -29,9 +29,12 @@ class RefMLP(nn.Module):  # dqn.py:72-93
 @pytest.mark.parametrize("dims,act,rows", [
     ([98, 256, 128, 64, 16, 6], nn.PReLU, 131072), ([98, 256, 128, 64, 16, 6], nn.PReLU, 1000), ([196, 32, 16, 6], nn.PReLU, 4099),
     ([98, 24, 5], nn.ReLU, 777), ([36, 200, 100, 7], nn.ReLU, 130), ([4, 6], nn.PReLU, 5), ([78, 64, 6], nn.PReLU, 1),
-    ([200, 150, 17, 129, 3], nn.PReLU, 515)])
-def test_fused_mlp_matches_the_module(cuda_lib, dims, act, rows):
+    ([200, 150, 17, 129, 3], nn.PReLU, 515), ([16, 400, 400, 2], nn.PReLU, 300)])
+@pytest.mark.parametrize("tile_rows", ["128", "64"])  # 256 threads, one CTA per SM / 128 threads, two CTAs per SM
+def test_fused_mlp_matches_the_module(cuda_lib, monkeypatch, dims, act, rows, tile_rows):
     import sus_net_b200 as S
+
+    monkeypatch.setenv("SUSNET_MLP_ROWS", tile_rows)  # ([16, 400, 400, 2] only fits as a 64-row tile: chosen automatically)
 
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda")
@@ -70,6 +73,6 @@ def test_fused_mlp_scope(cuda_lib):
     assert not S.FusedMLP.supports(nn.Conv2d(1, 1, 1)) and not S.FusedMLP.supports(None)
     with pytest.raises(NotImplementedError):
         S.FusedMLP(nn.Sequential(nn.Linear(4, 4), nn.Tanh(), nn.Linear(4, 2)))
-    big = RefMLP([16, 400, 400, 2]).to("cuda")  # two adjacent 400-wide layers: 410 KB of activations per row tile
+    big = RefMLP([16, 800, 800, 2]).to("cuda")  # two adjacent 800-wide layers: 410 KB of activations even per 64-row tile
     with pytest.raises(NotImplementedError):
         S.FusedMLP(big)(torch.zeros(4, 1, 1, device="cuda"), torch.zeros(4, 1, 16, device="cuda"))
