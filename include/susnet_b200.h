@@ -311,7 +311,8 @@ typedef struct SusReplayPush {
   int64_t N, M, idx;          /* transitions per launch, ring capacity, first slot */
   int32_t T, S, A, n_imposters;
   const float *seq_in;        /* [N][T][S] running state sequence of every env before the step */
-  float *seq_out;             /* [N][T][S] the sequence the next step starts from (must not alias seq_in) */
+  float *seq_out;             /* [N][T][S] the sequence the next step starts from (may be seq_in itself when T == 1,
+                                 must not alias it otherwise) */
   const float *next_flat;     /* [N][S] post-step, pre-reset state (SusStepIO.next_flat) */
   const float *cur_flat;      /* [N][S] state the next action is taken from (sus_env_export_flat) */
   const void *actions;        /* [N][A] */

@@ -178,7 +178,8 @@ extern "C" int sus_replay_push(const SusReplayPush* a, int device, void* stream)
   if (a->T * a->S < a->A || a->T * a->S < a->n_imposters)
     return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "replay push: sequence block smaller than the action row");
   if (a->N == 0) return SUS_OK;
-  if (!a->seq_in || !a->seq_out || a->seq_in == a->seq_out || !a->next_flat || !a->cur_flat || !a->actions || !a->rewards ||
+  // T == 1: every thread reads and writes its own elements of the sequence only, so it may be advanced in place
+  if (!a->seq_in || !a->seq_out || (a->seq_in == a->seq_out && a->T != 1) || !a->next_flat || !a->cur_flat || !a->actions || !a->rewards ||
       !a->done || !a->truncated || !a->imposters || !a->states || !a->r_actions || !a->r_rewards || !a->next_states ||
       !a->r_dones || !a->r_imposters)
     return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "replay push: NULL or aliased buffer");

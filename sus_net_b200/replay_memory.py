@@ -142,9 +142,11 @@ class ReplayBuffer:
         applied = env._applied_actions  # the device tensor the step consumed (given, converted, or drawn by the policy)
         env.flat_states(out=self._cur_flat)
         N = env.num_envs
+        # fixed pointers (graph replays) with T == 1: the kernel advances the sequence in place, no copy back
+        in_place = self._static and self.trajectory_size == 1
         p = L.SusReplayPush(
             N=N, M=self.max_size, idx=self.idx, T=self.trajectory_size, S=self.state_size, A=self.n_agents,
-            n_imposters=self.n_imposters, seq_in=self._seq[0].data_ptr(), seq_out=self._seq[1].data_ptr(),
+            n_imposters=self.n_imposters, seq_in=self._seq[0].data_ptr(), seq_out=self._seq[0 if in_place else 1].data_ptr(),
             next_flat=next_flat.data_ptr(), cur_flat=self._cur_flat.data_ptr(), actions=applied.data_ptr(),
             actions_dtype=_TORCH_TO_SUS[applied.dtype], rewards=rewards.data_ptr(), done=dones.data_ptr(),
             truncated=truncated.data_ptr(), imposters=env._imposters_buf.data_ptr(), states=self.states.data_ptr(),
@@ -153,7 +155,8 @@ class ReplayBuffer:
             idx_dev=self._idx_dev.data_ptr() if self._static else None)
         L.check(env.lib.sus_replay_push(C.byref(p), self.device.index, env._stream()))
         if self._static:  # same buffers every step (a graph replays fixed pointers): copy the rolled sequence back
-            self._seq[0].copy_(self._seq[1])
+            if not in_place:
+                self._seq[0].copy_(self._seq[1])
             self._idx_dev.add_(N).remainder_(self.max_size)
             self._size_dev.add_(N).clamp_(max=self.max_size)
         else:

@@ -70,9 +70,13 @@ def _case(rng, N, M, idx, T, S, A, n_imp, dtype, off):
     return ins, ring, want, want_seq
 
 
-def _run(fn, L, ins, ring, N, M, idx, T, S, A, n_imp, dtype, off, idx_dev):
+def _run(fn, L, ins, ring, N, M, idx, T, S, A, n_imp, dtype, off, idx_dev, in_place=False):
     out = {k: _off(v, off if v.dtype == np.float32 else 0) for k, v in ring.items()}
-    seq_out = _off(np.full((N, T, S), -5, np.float32), off)
+    if in_place:  # T == 1 only: the sequence is advanced where it stands
+        ins = dict(ins, seq=_off(ins["seq"], off))
+        seq_out = ins["seq"]
+    else:
+        seq_out = _off(np.full((N, T, S), -5, np.float32), off)
     code = {np.uint8: L.U8, np.int32: L.I32, np.int64: L.I64}[dtype]
     dev_idx = np.array([idx], np.int64)
     p = L.SusReplayPush(N=N, M=M, idx=0 if idx_dev else idx, T=T, S=S, A=A, n_imposters=n_imp, seq_in=ins["seq"].ctypes.data,
@@ -114,3 +118,6 @@ def test_vector_replay_push_equals_scalar_kernel_and_numpy(emu, shape):
                             assert np.array_equal(out[k], want[k]), (name, k, idx, dtype, off)
                         assert np.array_equal(seq_out, want_seq), (name, "seq_out", idx, dtype, off)
                         got[name] = out
+                        if T == 1:
+                            out, seq_out = _run(fn, L, ins, ring, N, M, idx, T, S, A, n_imp, dtype, off, idx_dev, in_place=True)
+                            assert all(np.array_equal(out[k], want[k]) for k in want) and np.array_equal(seq_out, want_seq)

@@ -53,10 +53,13 @@ def main():
         t = timed(lambda: m(sp, x))
         out["torch_tf32"] = {"ms": t, "tflops": flops / t / 1e9}
         torch.backends.cuda.matmul.allow_tf32 = False
-    t = timed(lambda: f(sp, x))
-    out["sus_mlp_forward_fp32"] = {"ms": t, "tflops": flops / t / 1e9}
-    err = float(((f(sp, x) - m(sp, x)).abs().max()).item())
-    out["max_abs_diff_vs_torch_fp32"] = err
+    os.environ["SUSNET_MLP_VERBOSE"] = "1"  # the 64-row geometry reports its CTAs per SM on stderr
+    for rows in ("128", "64"):  # 128-row tiles (256 threads, one CTA per SM) / 64-row tiles (128 threads, two CTAs per SM)
+        os.environ["SUSNET_MLP_ROWS"] = rows
+        t = timed(lambda: f(sp, x))
+        err = float(((f(sp, x) - m(sp, x)).abs().max()).item())
+        out[f"sus_mlp_forward_fp32_rows{rows}"] = {"ms": t, "tflops": flops / t / 1e9, "max_abs_diff_vs_torch_fp32": err}
+    os.environ.pop("SUSNET_MLP_ROWS")
     print(json.dumps(out))
 
 
