@@ -26,7 +26,8 @@ namespace {
 //   128 rows, 256 threads, ONE CTA per SM (213 KB of shared memory at cfg5);
 //    64 rows, 128 threads, TWO CTAs per SM (2 x 112.5 KB): the same eight warps per SM, but while one CTA stages its input tile,
 //    waits at a chunk barrier or runs the narrow tail layers the other one keeps the FFMA pipe busy (SUSNET_MLP_ROWS=64).
-constexpr int kKc = 16;  // k per weight chunk
+constexpr int kKc = 16;        // k per weight chunk (over all k-parts)
+constexpr int kDefaultSplit = 1;  // k-parts per CTA unless SUSNET_MLP_SPLIT says otherwise
 
 struct MlpParams {
   SusMlpSpec s;
@@ -38,7 +39,10 @@ struct MlpParams {
 
 // One layer on the CTA's row tile: out[m][r] = act(bias[m] + sum_k W[m][k] * in[k][r]) for m < M, or straight to global memory
 // for the last layer.  CT = columns per thread (column block = 16 * CT); M is processed in blocks of 16 * CT columns.
-template <int ROWS, int CT>
+// SPLIT = 2: the CTA has two PARTS of 2 * ROWS threads; both own the same (rows, columns) micro-tiles, each sums half of the k
+// range, part 1 leaves its partial sums in the layer's output region and part 0 adds them in its epilogue.  Twice the warps per
+// scheduler for the same registers per thread and the same operand loads per FFMA.
+template <int ROWS, int SPLIT, int CT>
 __device__ __forceinline__ void layer(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ alpha,
                                       int act, int K, int M, int in_off, int out_off,
                                       float* __restrict__ gout, int64_t row0, int64_t n_rows, int out_stride, int wst_off) {
@@ -47,43 +51,50 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
   extern __shared__ __align__(128) float smem[];
   const float* in = smem + in_off;
   float* outs = smem + out_off;
-  float* wst = smem + wst_off;
-  const int tid = threadIdx.x;
-  constexpr int kRows = ROWS, kThreads = 2 * ROWS, RG = ROWS / 8, HALF = ROWS / 2;
+  constexpr int kRows = ROWS, PT = 2 * ROWS, RG = ROWS / 8, HALF = ROWS / 2;  // PT: threads per part
+  constexpr int KC = kKc / SPLIT;                                              // k per chunk and part
+  const int part = SPLIT > 1 ? (int)threadIdx.x / PT : 0;
+  const int tid = SPLIT > 1 ? (int)threadIdx.x % PT : (int)threadIdx.x;        // thread within its part
   const int rg = tid % RG, cg = tid / RG;  // row group, column group (CT columns)
   // a thread's 8 rows are r0 .. r0+3 and HALF+r0 .. HALF+r0+3 with r0 = 4 * rg: the row-group threads of a (half-)warp read
   // contiguous bytes per LDS.128 (rows 8 * rg .. would put four threads on every bank: measured 22 TFLOP/s)
   const int r0 = rg * 4;
   constexpr int CB = 16 * CT;  // columns per block
+  constexpr int CBP = CB + 4;  // padded row of a staged chunk: conflict-free transposing stores
+  float* wst = smem + wst_off + part * (2 * KC * CBP);
   const float a = (act == SUS_ACT_PRELU && alpha) ? alpha[0] : 0.0f;
+  // this part's k range; every part runs the same number of chunks (and barriers), trailing ones may be short or empty
+  const int Kp = (K + SPLIT - 1) / SPLIT;
+  const int k_lo = part * Kp;
+  const int k_hi = k_lo + Kp < K ? k_lo + Kp : K;
+  const int n_chunks = (Kp + KC - 1) / KC;
   for (int m0 = 0; m0 < M; m0 += CB) {
     float acc[8][CT];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < CT; ++j) acc[i][j] = 0.0f;
-    const int n_chunks = (K + kKc - 1) / kKc;
-    constexpr int CBP = CB + 4;                  // padded row of a staged chunk: 2-way instead of 16-way bank conflicts
-    constexpr int PER = (CB * kKc + kThreads - 1) / kThreads;  // staged weights per thread and chunk (8 / 4 / 1)
+    constexpr int PER = (CB * KC + PT - 1) / PT;  // staged weights per thread and chunk
     float pre[PER];
-    // chunk c of the block: w[kk][col] = W[m0 + col][c * kKc + kk] (zero outside M / K).  Consecutive threads walk k, so the
-    // global reads are contiguous runs of a weight row; loaded into registers one chunk ahead, stored after the math.
+    // chunk c of the block: w[kk][col] = W[m0 + col][k_lo + c * KC + kk] (zero outside M / the part's k range).  Consecutive
+    // threads walk k, so the global reads are contiguous runs of a weight row; loaded into registers one chunk ahead, stored
+    // after the math.
     auto fetch = [&](int c) {
 #pragma unroll
       for (int q = 0; q < PER; ++q) {
-        const int idx = tid + q * kThreads;
-        const int col = idx / kKc, kk = idx - col * kKc;
-        const int m = m0 + col, k = c * kKc + kk;
-        pre[q] = (idx < CB * kKc && m < M && k < K) ? W[(int64_t)m * K + k] : 0.0f;
+        const int idx = tid + q * PT;
+        const int col = idx / KC, kk = idx - col * KC;
+        const int m = m0 + col, k = k_lo + c * KC + kk;
+        pre[q] = (idx < CB * KC && m < M && k < k_hi) ? W[(int64_t)m * K + k] : 0.0f;
       }
     };
     auto put = [&](int buf) {
-      float* dst = wst + buf * (kKc * CBP);
+      float* dst = wst + buf * (KC * CBP);
 #pragma unroll
       for (int q = 0; q < PER; ++q) {
-        const int idx = tid + q * kThreads;
-        const int col = idx / kKc, kk = idx - col * kKc;
-        if (idx < CB * kKc) dst[kk * CBP + col] = pre[q];
+        const int idx = tid + q * PT;
+        const int col = idx / KC, kk = idx - col * KC;
+        if (idx < CB * KC) dst[kk * CBP + col] = pre[q];
       }
     };
     fetch(0);
@@ -92,9 +103,10 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
     for (int c = 0; c < n_chunks; ++c) {
       const int buf = c & 1;
       if (c + 1 < n_chunks) fetch(c + 1);
-      const float* w = wst + buf * (kKc * CBP) + cg * CT;
-      const float* xin = in + (int64_t)(c * kKc) * kRows + r0;
-      const int kmax = K - c * kKc < kKc ? K - c * kKc : kKc;
+      const float* w = wst + buf * (KC * CBP) + cg * CT;
+      const float* xin = in + (int64_t)(k_lo + c * KC) * kRows + r0;
+      const int left = k_hi - (k_lo + c * KC);
+      const int kmax = left < KC ? (left < 0 ? 0 : left) : KC;
       auto kstep = [&](int kk) {
         const float4 x0 = *reinterpret_cast<const float4*>(xin + kk * kRows);
         const float4 x1 = *reinterpret_cast<const float4*>(xin + kk * kRows + HALF);
@@ -115,49 +127,76 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
 #pragma unroll
           for (int j = 0; j < CT; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
       };
-      if (kmax == kKc) {  // full chunk: straight-line code, the loads of the next k-steps overlap the FFMAs
+      if (kmax == KC) {  // full chunk: straight-line code, the loads of the next k-steps overlap the FFMAs
 #pragma unroll
-        for (int kk = 0; kk < kKc; ++kk) kstep(kk);
+        for (int kk = 0; kk < KC; ++kk) kstep(kk);
       } else {
         for (int kk = 0; kk < kmax; ++kk) kstep(kk);
       }
       if (c + 1 < n_chunks) put(buf ^ 1);  // (the other buffer was last read before the barrier that ended chunk c - 1)
       __syncthreads();
     }
-    // epilogue: bias + activation; to the next layer's k-major region, or (last layer) to global memory [row][out_stride]
+    if (SPLIT > 1) {  // part 1's partial sums travel through the (still unused) output positions of this column block
+      if (part == 1) {
 #pragma unroll
-    for (int j = 0; j < CT; ++j) {
-      const int m = m0 + cg * CT + j;
-      if (m >= M) continue;
-      const float b = bias ? bias[m] : 0.0f;
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float t = acc[i][j] + b;
-        if (act == SUS_ACT_RELU) t = t > 0.0f ? t : 0.0f;
-        else if (act == SUS_ACT_PRELU) t = t > 0.0f ? t : a * t;
-        v[i] = t;
+        for (int j = 0; j < CT; ++j) {
+          const int m = m0 + cg * CT + j;
+          if (m >= M) continue;
+          float* o = outs + (int64_t)m * kRows + r0;
+          *reinterpret_cast<float4*>(o) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+          *reinterpret_cast<float4*>(o + HALF) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
+        }
       }
-      if (gout) {
+      __syncthreads();
+      if (part == 0) {
+#pragma unroll
+        for (int j = 0; j < CT; ++j) {
+          const int m = m0 + cg * CT + j;
+          if (m >= M) continue;
+          const float* o = outs + (int64_t)m * kRows + r0;
+          const float4 p0 = *reinterpret_cast<const float4*>(o);
+          const float4 p1 = *reinterpret_cast<const float4*>(o + HALF);
+          acc[0][j] += p0.x; acc[1][j] += p0.y; acc[2][j] += p0.z; acc[3][j] += p0.w;
+          acc[4][j] += p1.x; acc[5][j] += p1.y; acc[6][j] += p1.z; acc[7][j] += p1.w;
+        }
+      }
+    }
+    // epilogue: bias + activation; to the next layer's k-major region, or (last layer) to global memory [row][out_stride]
+    if (part == 0) {
+#pragma unroll
+      for (int j = 0; j < CT; ++j) {
+        const int m = m0 + cg * CT + j;
+        if (m >= M) continue;
+        const float b = bias ? bias[m] : 0.0f;
+        float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int64_t row = row0 + r0 + (i & 3) + (i >> 2) * HALF;
-          if (row < n_rows) gout[row * out_stride + m] = v[i];
+          float t = acc[i][j] + b;
+          if (act == SUS_ACT_RELU) t = t > 0.0f ? t : 0.0f;
+          else if (act == SUS_ACT_PRELU) t = t > 0.0f ? t : a * t;
+          v[i] = t;
         }
-      } else {
-        float* o = outs + (int64_t)m * kRows + r0;
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + HALF) = make_float4(v[4], v[5], v[6], v[7]);
+        if (gout) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t row = row0 + r0 + (i & 3) + (i >> 2) * HALF;
+            if (row < n_rows) gout[row * out_stride + m] = v[i];
+          }
+        } else {
+          float* o = outs + (int64_t)m * kRows + r0;
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + HALF) = make_float4(v[4], v[5], v[6], v[7]);
+        }
       }
     }
   }
   __syncthreads();
 }
 
-template <int ROWS>
-__global__ void __launch_bounds__(2 * ROWS, ROWS == 64 ? 2 : 1) k_mlp_forward(const __grid_constant__ MlpParams p) {
+template <int ROWS, int SPLIT>
+__global__ void __launch_bounds__(2 * ROWS * SPLIT, ROWS == 64 ? 2 : 1) k_mlp_forward(const __grid_constant__ MlpParams p) {
   extern __shared__ __align__(128) float smem[];
-  constexpr int kRows = ROWS, kThreads = 2 * ROWS;
+  constexpr int kRows = ROWS, kThreads = 2 * ROWS * SPLIT;
   const int region_off[2] = {0, p.region_b_floats * kRows};  // [0]: even positions (input, h2, ...), [1]: odd
   const int wst_off = region_off[1] + p.region_a_floats * kRows;  // 2 x kKc x (128 + 4) floats
   float* region[2] = {smem + region_off[0], smem + region_off[1]};
@@ -183,9 +222,9 @@ __global__ void __launch_bounds__(2 * ROWS, ROWS == 64 ? 2 : 1) k_mlp_forward(co
         for (int64_t i = threadIdx.x; i < n_floats; i += kThreads) raw[i] = src[i];
       }
       __syncthreads();
-      const int r = threadIdx.x % kRows, half = threadIdx.x / kRows;
+      const int r = threadIdx.x % kRows, first = threadIdx.x / kRows;
       const bool ok = r < n_valid;
-      for (int k = half; k < K0; k += 2) region[0][(int64_t)k * kRows + r] = ok ? raw[(int64_t)r * K0 + k] : 0.0f;
+      for (int k = first; k < K0; k += kThreads / kRows) region[0][(int64_t)k * kRows + r] = ok ? raw[(int64_t)r * K0 + k] : 0.0f;
     }
     __syncthreads();
     for (int l = 0; l < s.n_layers; ++l) {
@@ -195,11 +234,36 @@ __global__ void __launch_bounds__(2 * ROWS, ROWS == 64 ? 2 : 1) k_mlp_forward(co
       const int outs = (l & 1) ? region_off[0] : region_off[1];
       const int act = last ? SUS_ACT_NONE : s.activation;
       float* gout = last ? p.out : nullptr;
-      if (M > 64) layer<ROWS, 8>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
-      else if (M > 16) layer<ROWS, 4>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
-      else layer<ROWS, 1>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      if (M > 64) layer<ROWS, SPLIT, 8>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      else if (M > 16) layer<ROWS, SPLIT, 4>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      else layer<ROWS, SPLIT, 1>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
     }
   }
+}
+
+// one geometry: grants the dynamic shared memory once per device and size, sizes the persistent grid, launches
+template <int ROWS, int SPLIT>
+cudaError_t launch_geometry(const MlpParams& p, size_t smem, int device, int sms, cudaStream_t stream, bool verbose) {
+  constexpr int kThreads = 2 * ROWS * SPLIT;
+  static size_t granted[64] = {};
+  static int ctas_per_sm[64] = {};
+  const int d = device >= 0 && device < 64 ? device : 0;
+  if (granted[d] != smem) {  // (re)query: the CTAs per SM depend on the size
+    cudaFuncSetAttribute(k_mlp_forward<ROWS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ROWS == 64)
+      cudaFuncSetAttribute(k_mlp_forward<ROWS, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 1;  // 64-row tiles: 2 when two tiles' activations fit on an SM (cfg5: 2 x 112.5 KB)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mlp_forward<ROWS, SPLIT>, kThreads, smem);
+    ctas_per_sm[d] = per_sm < 1 ? 1 : per_sm;
+    granted[d] = smem;
+    if (verbose)
+      fprintf(stderr, "sus_mlp_forward: %d-row tiles, %d threads, %zu bytes of shared memory, %d CTAs per SM\n", ROWS, kThreads, smem,
+              ctas_per_sm[d]);
+  }
+  const int64_t tiles = (p.n_rows + ROWS - 1) / ROWS;
+  const int64_t grid = (int64_t)sms * ctas_per_sm[d];
+  k_mlp_forward<ROWS, SPLIT><<<(unsigned)(tiles < grid ? tiles : grid), kThreads, smem, stream>>>(p);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -209,11 +273,12 @@ extern "C" int sus_mlp_forward(const SusMlpSpec* spec, const float* x, int64_t n
   if (spec->n_layers < 1 || spec->n_layers > SUS_MLP_MAX_LAYERS) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: 1..8 layers");
   if (spec->activation < SUS_ACT_NONE || spec->activation > SUS_ACT_PRELU)
     return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: unknown activation");
-  int a = 0, b = 0;  // widest activation at odd / even positions of the chain (the last layer's output goes to global memory)
+  // widest activation at odd / even positions of the chain.  The last layer's output goes to global memory, but with two
+  // k-parts its partial sums pass through the region it would occupy, so it is counted as well.
+  int a = 0, b = 0;
   for (int l = 0; l <= spec->n_layers; ++l) {
     if (spec->dims[l] < 1) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: layer width < 1");
     if (l < spec->n_layers && !spec->weight[l]) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: NULL weight");
-    if (l == spec->n_layers) break;
     if (l & 1) { if (spec->dims[l] > a) a = spec->dims[l]; } else { if (spec->dims[l] > b) b = spec->dims[l]; }
   }
   if (a < spec->dims[0]) a = spec->dims[0];  // region 1 also stages the raw (row-major) input tile before layer 0 runs
@@ -224,49 +289,25 @@ extern "C" int sus_mlp_forward(const SusMlpSpec* spec, const float* x, int64_t n
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   auto smem_of = [&](int rows) { return ((size_t)(a + b) * rows + 2 * kKc * 132) * sizeof(float); };
-  const char* rows_env = getenv("SUSNET_MLP_ROWS");  // read per call: tests and tools switch geometries inside one process
-  // 128-row tiles unless asked for 64-row tiles, or unless only a 64-row tile of the two widest adjacent layers fits
+  // geometry knobs, read per call (tests and tools switch inside one process): SUSNET_MLP_ROWS = 64 | 128 rows per tile,
+  // SUSNET_MLP_SPLIT = 1 | 2 k-parts.  128-row tiles unless only a 64-row tile of the two widest adjacent layers fits.
+  const char* rows_env = getenv("SUSNET_MLP_ROWS");
+  const char* split_env = getenv("SUSNET_MLP_SPLIT");
   const int rows = ((rows_env && atoi(rows_env) == 64) || smem_of(128) > (size_t)max_smem) ? 64 : 128;
+  const int split = split_env ? (atoi(split_env) == 2 ? 2 : 1) : kDefaultSplit;
   const size_t smem = smem_of(rows);
   int rc = SUS_OK;
   if (smem > (size_t)max_smem) {
     rc = sus_internal_fail(SUS_ERR_UNSUPPORTED, "mlp_forward: the two widest adjacent layers do not fit in shared memory (run the module itself)");
   } else if (n_rows > 0) {
-    static size_t granted[2][64] = {};
-    const int v = rows == 64;
-    if (device >= 0 && device < 64 && granted[v][device] < smem) {
-      if (v) {
-        cudaFuncSetAttribute(k_mlp_forward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_mlp_forward<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      } else {
-        cudaFuncSetAttribute(k_mlp_forward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      }
-      granted[v][device] = smem;
-    }
     MlpParams p;
     p.s = *spec; p.x = x; p.out = out; p.n_rows = n_rows; p.region_a_floats = a; p.region_b_floats = b;
-    const int64_t tiles = (n_rows + rows - 1) / rows;
-    if (v) {
-      // CTAs per SM: 2 when two tiles' activations fit on an SM (cfg5: 2 x 112.5 KB); queried once per (device, size)
-      static size_t occ_smem[64] = {};
-      static int occ_ctas[64] = {};
-      int per_sm = 1;
-      if (device >= 0 && device < 64 && occ_smem[device] == smem) {
-        per_sm = occ_ctas[device];
-      } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mlp_forward<64>, 128, smem);
-        if (per_sm < 1) per_sm = 1;
-        if (device >= 0 && device < 64) { occ_smem[device] = smem; occ_ctas[device] = per_sm; }
-      }
-      static const bool verbose = getenv("SUSNET_MLP_VERBOSE") != nullptr;
-      if (verbose) fprintf(stderr, "sus_mlp_forward: 64-row tiles, %zu bytes of shared memory, %d CTAs per SM\n", smem, per_sm);
-      const int64_t grid = (int64_t)sms * per_sm;
-      k_mlp_forward<64><<<(unsigned)(tiles < grid ? tiles : grid), 128, smem, (cudaStream_t)stream>>>(p);
-    } else {
-      k_mlp_forward<128><<<(unsigned)(tiles < sms ? tiles : sms), 256, smem, (cudaStream_t)stream>>>(p);
-    }
+    static const bool verbose = getenv("SUSNET_MLP_VERBOSE") != nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t err;
+    if (rows == 128) err = split == 2 ? launch_geometry<128, 2>(p, smem, device, sms, st, verbose) : launch_geometry<128, 1>(p, smem, device, sms, st, verbose);
+    else err = split == 2 ? launch_geometry<64, 2>(p, smem, device, sms, st, verbose) : launch_geometry<64, 1>(p, smem, device, sms, st, verbose);
     sus_internal_count_launch();
-    const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) rc = sus_internal_fail(SUS_ERR_CUDA, cudaGetErrorString(err));
   }
   if (prev != device && prev >= 0) cudaSetDevice(prev);

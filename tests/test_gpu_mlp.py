@@ -30,11 +30,13 @@ class RefMLP(nn.Module):  # dqn.py:72-93
     ([98, 256, 128, 64, 16, 6], nn.PReLU, 131072), ([98, 256, 128, 64, 16, 6], nn.PReLU, 1000), ([196, 32, 16, 6], nn.PReLU, 4099),
     ([98, 24, 5], nn.ReLU, 777), ([36, 200, 100, 7], nn.ReLU, 130), ([4, 6], nn.PReLU, 5), ([78, 64, 6], nn.PReLU, 1),
     ([200, 150, 17, 129, 3], nn.PReLU, 515), ([16, 400, 400, 2], nn.PReLU, 300)])
-@pytest.mark.parametrize("tile_rows", ["128", "64"])  # 256 threads, one CTA per SM / 128 threads, two CTAs per SM
-def test_fused_mlp_matches_the_module(cuda_lib, monkeypatch, dims, act, rows, tile_rows):
+@pytest.mark.parametrize("tile_rows,k_parts", [("128", "1"), ("128", "2"), ("64", "1"), ("64", "2")])
+def test_fused_mlp_matches_the_module(cuda_lib, monkeypatch, dims, act, rows, tile_rows, k_parts):
+    """Every geometry of the kernel: 128-row tiles (one CTA per SM) or 64-row tiles (two), one or two k-parts per CTA."""
     import sus_net_b200 as S
 
     monkeypatch.setenv("SUSNET_MLP_ROWS", tile_rows)  # ([16, 400, 400, 2] only fits as a 64-row tile: chosen automatically)
+    monkeypatch.setenv("SUSNET_MLP_SPLIT", k_parts)
 
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda")

@@ -53,13 +53,16 @@ def main():
         t = timed(lambda: m(sp, x))
         out["torch_tf32"] = {"ms": t, "tflops": flops / t / 1e9}
         torch.backends.cuda.matmul.allow_tf32 = False
-    os.environ["SUSNET_MLP_VERBOSE"] = "1"  # the 64-row geometry reports its CTAs per SM on stderr
-    for rows in ("128", "64"):  # 128-row tiles (256 threads, one CTA per SM) / 64-row tiles (128 threads, two CTAs per SM)
-        os.environ["SUSNET_MLP_ROWS"] = rows
-        t = timed(lambda: f(sp, x))
-        err = float(((f(sp, x) - m(sp, x)).abs().max()).item())
-        out[f"sus_mlp_forward_fp32_rows{rows}"] = {"ms": t, "tflops": flops / t / 1e9, "max_abs_diff_vs_torch_fp32": err}
-    os.environ.pop("SUSNET_MLP_ROWS")
+    os.environ["SUSNET_MLP_VERBOSE"] = "1"  # every geometry reports its threads and CTAs per SM on stderr
+    for rows in ("128", "64"):  # 128-row tiles (one CTA per SM) / 64-row tiles (two CTAs per SM)
+        for split in ("1", "2"):  # k-parts per CTA (2: twice the warps, each summing half of k)
+            os.environ["SUSNET_MLP_ROWS"], os.environ["SUSNET_MLP_SPLIT"] = rows, split
+            t = timed(lambda: f(sp, x))
+            err = float(((f(sp, x) - m(sp, x)).abs().max()).item())
+            out[f"sus_mlp_forward_fp32_rows{rows}_split{split}"] = {"ms": t, "tflops": flops / t / 1e9, "max_abs_diff_vs_torch_fp32": err}
+    os.environ.pop("SUSNET_MLP_ROWS"); os.environ.pop("SUSNET_MLP_SPLIT")
+    t = timed(lambda: f(sp, x))
+    out["sus_mlp_forward_fp32_default"] = {"ms": t, "tflops": flops / t / 1e9}
     print(json.dumps(out))
 
 
