@@ -22,7 +22,8 @@ EXPORTED_SYMBOLS = (
     "sus_env_get_ticks", "sus_env_set_ticks", "sus_env_state_arrays", "sus_env_debug_inject_words",
     "sus_launch_count", "sus_replay_push", "sus_env_rollout", "sus_env_track_returns", "sus_env_return_sums",
     "sus_env_device_ticks", "sus_alloc_compressible", "sus_free_compressible", "sus_compact_layout", "sus_reward_lut",
-    "sus_env_select_actions", "sus_seq_roll", "sus_env_aux_arrays", "sus_mlp_forward",
+    "sus_env_select_actions", "sus_seq_roll", "sus_env_aux_arrays", "sus_mlp_forward", "sus_mlp_workspace_bytes",
+    "sus_mlp_forward_ws",
     "sus_host_pack_actions", "sus_host_decode_results",
 )
 
@@ -148,6 +149,8 @@ def lib():
         "sus_env_select_actions": ([vp, C.POINTER(SusPolicyIO), vp], C.c_int),
         "sus_seq_roll": ([vp, vp, vp, vp, vp, i64, i64, i32, i32, C.c_int, vp], C.c_int),
         "sus_mlp_forward": ([C.POINTER(SusMlpSpec), vp, i64, vp, C.c_int, vp], C.c_int),
+        "sus_mlp_workspace_bytes": ([C.POINTER(SusMlpSpec)], i64),
+        "sus_mlp_forward_ws": ([C.POINTER(SusMlpSpec), vp, i64, vp, vp, i64, C.c_int, vp], C.c_int),
         "sus_host_pack_actions": ([C.POINTER(SusConfig), vp, i32, i64, vp, i32], C.c_int),
         "sus_host_decode_results": ([C.POINTER(SusConfig), vp, i64, vp, i32, vp, vp, i32], C.c_int),
     }

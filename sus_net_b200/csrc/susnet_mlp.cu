@@ -35,15 +35,28 @@ struct MlpParams {
   float* out;
   int64_t n_rows;
   int32_t region_a_floats, region_b_floats;  // activations regions (per row-tile): dims at odd / even positions
+  const float* packed;                        // repacked weights (k_mlp_pack) or NULL: stage from the torch layout
+  int64_t packed_off[SUS_MLP_MAX_LAYERS];     // float offset of every layer inside `packed`
 };
+
+// columns per thread of a layer with M outputs (column block = 16 * CT): the same rule in the kernel, the packer and the host
+__host__ __device__ inline int mlp_ct(int M) { return M > 64 ? 8 : (M > 16 ? 4 : 1); }
+// floats of one layer in the packed image: [column block][chunk of kKc k's][kk][column], zero outside M / K
+__host__ __device__ inline int64_t mlp_packed_floats(int K, int M) {
+  const int CB = 16 * mlp_ct(M);
+  return (int64_t)((M + CB - 1) / CB) * CB * ((K + 16 - 1) / 16) * 16;
+}
 
 // One layer on the CTA's row tile: out[m][r] = act(bias[m] + sum_k W[m][k] * in[k][r]) for m < M, or straight to global memory
 // for the last layer.  CT = columns per thread (column block = 16 * CT); M is processed in blocks of 16 * CT columns.
 // SPLIT = 2: the CTA has two PARTS of 2 * ROWS threads; both own the same (rows, columns) micro-tiles, each sums half of the k
 // range, part 1 leaves its partial sums in the layer's output region and part 0 adds them in its epilogue.  Twice the warps per
 // scheduler for the same registers per thread and the same operand loads per FFMA.
-template <int ROWS, int SPLIT, int CT>
-__device__ __forceinline__ void layer(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ alpha,
+// PACKED: the layer's weights come from the repacked image (k_mlp_pack): a chunk is CB * kKc contiguous floats that are copied
+// with 128-bit loads and stores -- 4 instructions per 4 weights instead of ~12 per weight for the transposing gather from the
+// torch layout (address arithmetic, bounds tests), which was 10 % of the kernel's issue slots (ncu source counters).
+template <int ROWS, int SPLIT, int CT, bool PACKED>
+__device__ __forceinline__ void layer(const float* __restrict__ W, const float* __restrict__ Wp, const float* __restrict__ bias, const float* __restrict__ alpha,
                                       int act, int K, int M, int in_off, int out_off,
                                       float* __restrict__ gout, int64_t row0, int64_t n_rows, int out_stride, int wst_off) {
   // offsets into the dynamic shared array, NOT generic pointers: with pointers picked from a runtime-indexed table the compiler
@@ -74,27 +87,46 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < CT; ++j) acc[i][j] = 0.0f;
-    constexpr int PER = (CB * KC + PT - 1) / PT;  // staged weights per thread and chunk
-    float pre[PER];
-    // chunk c of the block: w[kk][col] = W[m0 + col][k_lo + c * KC + kk] (zero outside M / the part's k range).  Consecutive
-    // threads walk k, so the global reads are contiguous runs of a weight row; loaded into registers one chunk ahead, stored
-    // after the math.
+    constexpr int PER = PACKED ? (CB * KC / 4 + PT - 1) / PT : (CB * KC + PT - 1) / PT;  // staged float4s / floats per thread and chunk
+    float4 pre4[PACKED ? PER : 1];
+    float pre[PACKED ? 1 : PER];
+    // chunk c of the block: w[kk][col] = W[m0 + col][k_lo + c * KC + kk] (zero outside M / the part's k range).
+    // Unpacked: consecutive threads walk k, so the global reads are contiguous runs of a weight row.  Either way the chunk is
+    // loaded into registers one chunk ahead and stored after the math.
+    const float4* wp4 = PACKED ? reinterpret_cast<const float4*>(Wp + (int64_t)(m0 / CB) * ((K + kKc - 1) / kKc) * (kKc * CB)) : nullptr;
     auto fetch = [&](int c) {
+      if constexpr (PACKED) {
 #pragma unroll
-      for (int q = 0; q < PER; ++q) {
-        const int idx = tid + q * PT;
-        const int col = idx / KC, kk = idx - col * KC;
-        const int m = m0 + col, k = k_lo + c * KC + kk;
-        pre[q] = (idx < CB * KC && m < M && k < k_hi) ? W[(int64_t)m * K + k] : 0.0f;
+        for (int q = 0; q < PER; ++q) {
+          const int f = tid + q * PT;
+          if (f < CB * KC / 4) pre4[q] = wp4[c * (CB * KC / 4) + f];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int idx = tid + q * PT;
+          const int col = idx / KC, kk = idx - col * KC;
+          const int m = m0 + col, k = k_lo + c * KC + kk;
+          pre[q] = (idx < CB * KC && m < M && k < k_hi) ? W[(int64_t)m * K + k] : 0.0f;
+        }
       }
     };
     auto put = [&](int buf) {
       float* dst = wst + buf * (KC * CBP);
+      if constexpr (PACKED) {
 #pragma unroll
-      for (int q = 0; q < PER; ++q) {
-        const int idx = tid + q * PT;
-        const int col = idx / KC, kk = idx - col * KC;
-        if (idx < CB * KC) dst[kk * CBP + col] = pre[q];
+        for (int q = 0; q < PER; ++q) {
+          const int f = tid + q * PT;
+          const int kk = f / (CB / 4), c4 = f - kk * (CB / 4);
+          if (f < CB * KC / 4) *reinterpret_cast<float4*>(dst + kk * CBP + c4 * 4) = pre4[q];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int idx = tid + q * PT;
+          const int col = idx / KC, kk = idx - col * KC;
+          if (idx < CB * KC) dst[kk * CBP + col] = pre[q];
+        }
       }
     };
     fetch(0);
@@ -193,7 +225,7 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
   __syncthreads();
 }
 
-template <int ROWS, int SPLIT>
+template <int ROWS, int SPLIT, bool PACKED>
 __global__ void __launch_bounds__(2 * ROWS * SPLIT, ROWS == 64 ? 2 : 1) k_mlp_forward(const __grid_constant__ MlpParams p) {
   extern __shared__ __align__(128) float smem[];
   constexpr int kRows = ROWS, kThreads = 2 * ROWS * SPLIT;
@@ -234,54 +266,92 @@ __global__ void __launch_bounds__(2 * ROWS * SPLIT, ROWS == 64 ? 2 : 1) k_mlp_fo
       const int outs = (l & 1) ? region_off[0] : region_off[1];
       const int act = last ? SUS_ACT_NONE : s.activation;
       float* gout = last ? p.out : nullptr;
-      if (M > 64) layer<ROWS, SPLIT, 8>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
-      else if (M > 16) layer<ROWS, SPLIT, 4>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
-      else layer<ROWS, SPLIT, 1>(s.weight[l], s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      const float* wp = PACKED ? p.packed + p.packed_off[l] : nullptr;
+      if (M > 64) layer<ROWS, SPLIT, 8, PACKED>(s.weight[l], wp, s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      else if (M > 16) layer<ROWS, SPLIT, 4, PACKED>(s.weight[l], wp, s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
+      else layer<ROWS, SPLIT, 1, PACKED>(s.weight[l], wp, s.bias[l], s.alpha[l], act, K, M, in, outs, gout, row0, p.n_rows, M, wst_off);
     }
   }
 }
 
+// Weights of every layer -> the packed image (see mlp_packed_floats): one thread per packed float.  The live parameters change
+// with every optimizer step, so this runs in front of every forward that was given a workspace (67 k floats at cfg5: ~3 us).
+__global__ void __launch_bounds__(256) k_mlp_pack(const __grid_constant__ MlpParams p, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  int l = 0;
+  while (l + 1 < p.s.n_layers && i >= p.packed_off[l + 1]) ++l;
+  const int K = p.s.dims[l], M = p.s.dims[l + 1];
+  const int CB = 16 * mlp_ct(M);
+  const int n_chunks = (K + kKc - 1) / kKc;
+  int64_t r = i - p.packed_off[l];
+  const int col = (int)(r % CB); r /= CB;
+  const int kk = (int)(r % kKc); r /= kKc;
+  const int c = (int)(r % n_chunks);
+  const int mb = (int)(r / n_chunks);
+  const int m = mb * CB + col, k = c * kKc + kk;
+  const_cast<float*>(p.packed)[i] = (m < M && k < K) ? p.s.weight[l][(int64_t)m * K + k] : 0.0f;
+}
+
 // one geometry: grants the dynamic shared memory once per device and size, sizes the persistent grid, launches
-template <int ROWS, int SPLIT>
+template <int ROWS, int SPLIT, bool PACKED>
 cudaError_t launch_geometry(const MlpParams& p, size_t smem, int device, int sms, cudaStream_t stream, bool verbose) {
   constexpr int kThreads = 2 * ROWS * SPLIT;
   static size_t granted[64] = {};
   static int ctas_per_sm[64] = {};
   const int d = device >= 0 && device < 64 ? device : 0;
   if (granted[d] != smem) {  // (re)query: the CTAs per SM depend on the size
-    cudaFuncSetAttribute(k_mlp_forward<ROWS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_mlp_forward<ROWS, SPLIT, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ROWS == 64)
-      cudaFuncSetAttribute(k_mlp_forward<ROWS, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k_mlp_forward<ROWS, SPLIT, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 1;  // 64-row tiles: 2 when two tiles' activations fit on an SM (cfg5: 2 x 112.5 KB)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mlp_forward<ROWS, SPLIT>, kThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mlp_forward<ROWS, SPLIT, PACKED>, kThreads, smem);
     ctas_per_sm[d] = per_sm < 1 ? 1 : per_sm;
     granted[d] = smem;
     if (verbose)
-      fprintf(stderr, "sus_mlp_forward: %d-row tiles, %d threads, %zu bytes of shared memory, %d CTAs per SM\n", ROWS, kThreads, smem,
-              ctas_per_sm[d]);
+      fprintf(stderr, "sus_mlp_forward: %d-row tiles, %d threads, %zu bytes of shared memory, %d CTAs per SM, %s weights\n", ROWS, kThreads,
+              smem, ctas_per_sm[d], PACKED ? "packed" : "torch-layout");
   }
   const int64_t tiles = (p.n_rows + ROWS - 1) / ROWS;
   const int64_t grid = (int64_t)sms * ctas_per_sm[d];
-  k_mlp_forward<ROWS, SPLIT><<<(unsigned)(tiles < grid ? tiles : grid), kThreads, smem, stream>>>(p);
+  k_mlp_forward<ROWS, SPLIT, PACKED><<<(unsigned)(tiles < grid ? tiles : grid), kThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-}  // namespace
-
-extern "C" int sus_mlp_forward(const SusMlpSpec* spec, const float* x, int64_t n_rows, float* out, int device, void* stream) {
-  if (!spec || (n_rows > 0 && (!x || !out))) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: NULL argument");
+// validates the chain; a / b = widest activation at odd / even positions.  The last layer's output goes to global memory, but
+// with two k-parts its partial sums pass through the region it would occupy, so it is counted as well.
+int check_spec(const SusMlpSpec* spec, int& a, int& b) {
+  if (!spec) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: NULL argument");
   if (spec->n_layers < 1 || spec->n_layers > SUS_MLP_MAX_LAYERS) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: 1..8 layers");
   if (spec->activation < SUS_ACT_NONE || spec->activation > SUS_ACT_PRELU)
     return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: unknown activation");
-  // widest activation at odd / even positions of the chain.  The last layer's output goes to global memory, but with two
-  // k-parts its partial sums pass through the region it would occupy, so it is counted as well.
-  int a = 0, b = 0;
+  a = b = 0;
   for (int l = 0; l <= spec->n_layers; ++l) {
     if (spec->dims[l] < 1) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: layer width < 1");
     if (l < spec->n_layers && !spec->weight[l]) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: NULL weight");
     if (l & 1) { if (spec->dims[l] > a) a = spec->dims[l]; } else { if (spec->dims[l] > b) b = spec->dims[l]; }
   }
   if (a < spec->dims[0]) a = spec->dims[0];  // region 1 also stages the raw (row-major) input tile before layer 0 runs
+  return SUS_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t sus_mlp_workspace_bytes(const SusMlpSpec* spec) {
+  int a, b;
+  if (check_spec(spec, a, b) != SUS_OK) return 0;
+  int64_t floats = 0;
+  for (int l = 0; l < spec->n_layers; ++l) floats += mlp_packed_floats(spec->dims[l], spec->dims[l + 1]);
+  return floats * (int64_t)sizeof(float);
+}
+
+extern "C" int sus_mlp_forward_ws(const SusMlpSpec* spec, const float* x, int64_t n_rows, float* out, void* workspace,
+                                  int64_t workspace_bytes, int device, void* stream) {
+  if (n_rows > 0 && (!x || !out)) return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: NULL argument");
+  int a, b;
+  if (int rc = check_spec(spec, a, b)) return rc;
+  if (workspace && (workspace_bytes < sus_mlp_workspace_bytes(spec) || (reinterpret_cast<uintptr_t>(workspace) & 15u)))
+    return sus_internal_fail(SUS_ERR_INVALID_ARGUMENT, "mlp_forward: workspace smaller than sus_mlp_workspace_bytes() or not 16-byte aligned");
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != device) cudaSetDevice(device);
@@ -290,11 +360,14 @@ extern "C" int sus_mlp_forward(const SusMlpSpec* spec, const float* x, int64_t n
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   auto smem_of = [&](int rows) { return ((size_t)(a + b) * rows + 2 * kKc * 132) * sizeof(float); };
   // geometry knobs, read per call (tests and tools switch inside one process): SUSNET_MLP_ROWS = 64 | 128 rows per tile,
-  // SUSNET_MLP_SPLIT = 1 | 2 k-parts.  128-row tiles unless only a 64-row tile of the two widest adjacent layers fits.
+  // SUSNET_MLP_SPLIT = 1 | 2 k-parts, SUSNET_MLP_PACKED = 0 ignores the workspace.  128-row tiles unless only a 64-row tile of
+  // the two widest adjacent layers fits.
   const char* rows_env = getenv("SUSNET_MLP_ROWS");
   const char* split_env = getenv("SUSNET_MLP_SPLIT");
+  const char* packed_env = getenv("SUSNET_MLP_PACKED");
   const int rows = ((rows_env && atoi(rows_env) == 64) || smem_of(128) > (size_t)max_smem) ? 64 : 128;
   const int split = split_env ? (atoi(split_env) == 2 ? 2 : 1) : kDefaultSplit;
+  const bool packed = workspace && split == 1 && !(packed_env && atoi(packed_env) == 0);  // (the packed chunks follow one k-part)
   const size_t smem = smem_of(rows);
   int rc = SUS_OK;
   if (smem > (size_t)max_smem) {
@@ -302,14 +375,36 @@ extern "C" int sus_mlp_forward(const SusMlpSpec* spec, const float* x, int64_t n
   } else if (n_rows > 0) {
     MlpParams p;
     p.s = *spec; p.x = x; p.out = out; p.n_rows = n_rows; p.region_a_floats = a; p.region_b_floats = b;
+    p.packed = packed ? static_cast<const float*>(workspace) : nullptr;
+    int64_t off = 0;
+    for (int l = 0; l < SUS_MLP_MAX_LAYERS; ++l) {
+      p.packed_off[l] = off;
+      if (l < spec->n_layers) off += mlp_packed_floats(spec->dims[l], spec->dims[l + 1]);
+    }
     static const bool verbose = getenv("SUSNET_MLP_VERBOSE") != nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t err;
-    if (rows == 128) err = split == 2 ? launch_geometry<128, 2>(p, smem, device, sms, st, verbose) : launch_geometry<128, 1>(p, smem, device, sms, st, verbose);
-    else err = split == 2 ? launch_geometry<64, 2>(p, smem, device, sms, st, verbose) : launch_geometry<64, 1>(p, smem, device, sms, st, verbose);
-    sus_internal_count_launch();
+    cudaError_t err = cudaSuccess;
+    if (packed) {
+      k_mlp_pack<<<(unsigned)((off + 255) / 256), 256, 0, st>>>(p, off);
+      sus_internal_count_launch();
+      err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) {
+      if (rows == 128) {
+        if (packed) err = launch_geometry<128, 1, true>(p, smem, device, sms, st, verbose);
+        else err = split == 2 ? launch_geometry<128, 2, false>(p, smem, device, sms, st, verbose) : launch_geometry<128, 1, false>(p, smem, device, sms, st, verbose);
+      } else {
+        if (packed) err = launch_geometry<64, 1, true>(p, smem, device, sms, st, verbose);
+        else err = split == 2 ? launch_geometry<64, 2, false>(p, smem, device, sms, st, verbose) : launch_geometry<64, 1, false>(p, smem, device, sms, st, verbose);
+      }
+      sus_internal_count_launch();
+    }
     if (err != cudaSuccess) rc = sus_internal_fail(SUS_ERR_CUDA, cudaGetErrorString(err));
   }
   if (prev != device && prev >= 0) cudaSetDevice(prev);
   return rc;
+}
+
+extern "C" int sus_mlp_forward(const SusMlpSpec* spec, const float* x, int64_t n_rows, float* out, int device, void* stream) {
+  return sus_mlp_forward_ws(spec, x, n_rows, out, nullptr, 0, device, stream);
 }

@@ -45,6 +45,7 @@ class FusedMLP:
         self.linears, self.acts = st
         self.activation = L.ACT_NONE if not self.acts else (L.ACT_PRELU if isinstance(self.acts[0], nn.PReLU) else L.ACT_RELU)
         self.in_features, self.out_features = self.linears[0].in_features, self.linears[-1].out_features
+        self._workspace = None  # device scratch for the repacked weights (owned here: one network, one stream at a time)
 
     @staticmethod
     def supports(module):
@@ -74,6 +75,11 @@ class FusedMLP:
             out = torch.empty((B, self.out_features), dtype=torch.float32, device=dev)
         spec = self._spec()
         lib = L.lib()
-        L.check(lib.sus_mlp_forward(C.byref(spec), C.c_void_p(x.data_ptr()), B, C.c_void_p(out.data_ptr()), dev.index,
-                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        if self._workspace is None or self._workspace.device != dev:
+            # allocated at the first call (outside any CUDA-graph capture in the training loop, whose warm-up runs eagerly)
+            n = int(lib.sus_mlp_workspace_bytes(C.byref(spec)))
+            self._workspace = torch.empty(max(n, 16), dtype=torch.uint8, device=dev)
+        L.check(lib.sus_mlp_forward_ws(C.byref(spec), C.c_void_p(x.data_ptr()), B, C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(), dev.index,
+                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         return out

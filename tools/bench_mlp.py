@@ -54,13 +54,14 @@ def main():
         out["torch_tf32"] = {"ms": t, "tflops": flops / t / 1e9}
         torch.backends.cuda.matmul.allow_tf32 = False
     os.environ["SUSNET_MLP_VERBOSE"] = "1"  # every geometry reports its threads and CTAs per SM on stderr
-    for rows in ("128", "64"):  # 128-row tiles (one CTA per SM) / 64-row tiles (two CTAs per SM)
-        for split in ("1", "2"):  # k-parts per CTA (2: twice the warps, each summing half of k)
-            os.environ["SUSNET_MLP_ROWS"], os.environ["SUSNET_MLP_SPLIT"] = rows, split
-            t = timed(lambda: f(sp, x))
-            err = float(((f(sp, x) - m(sp, x)).abs().max()).item())
-            out[f"sus_mlp_forward_fp32_rows{rows}_split{split}"] = {"ms": t, "tflops": flops / t / 1e9, "max_abs_diff_vs_torch_fp32": err}
-    os.environ.pop("SUSNET_MLP_ROWS"); os.environ.pop("SUSNET_MLP_SPLIT")
+    # rows per tile (128: one CTA per SM, 64: two), k-parts per CTA, weights staged from the repacked workspace image or not
+    for rows, split, packed in (("128", "1", "1"), ("128", "1", "0"), ("128", "2", "0"), ("64", "1", "1"), ("64", "1", "0"), ("64", "2", "0")):
+        os.environ["SUSNET_MLP_ROWS"], os.environ["SUSNET_MLP_SPLIT"], os.environ["SUSNET_MLP_PACKED"] = rows, split, packed
+        t = timed(lambda: f(sp, x))
+        err = float(((f(sp, x) - m(sp, x)).abs().max()).item())
+        out[f"sus_mlp_forward_fp32_rows{rows}_split{split}_packed{packed}"] = {"ms": t, "tflops": flops / t / 1e9, "max_abs_diff_vs_torch_fp32": err}
+    for k in ("SUSNET_MLP_ROWS", "SUSNET_MLP_SPLIT", "SUSNET_MLP_PACKED"):
+        os.environ.pop(k)
     t = timed(lambda: f(sp, x))
     out["sus_mlp_forward_fp32_default"] = {"ms": t, "tflops": flops / t / 1e9}
     print(json.dumps(out))
