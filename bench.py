@@ -519,8 +519,65 @@ def small_kernels(S, dev, K, peak):
                              "achieved_gbs": b_push * N / (ms_p * 1e-3) / 1e9}}
     for v in out.values():
         v["frac_of_hbm_copy_peak"] = v["achieved_gbs"] / peak
+    out["k_replay_push"]["kernel"] = "k_replay_push_v (128-bit streams + per-agent rows; round 1's one-thread-per-float kernel: 0.344 ms)"
     del env, buf
+    try:
+        out["k_mlp_forward"] = mlp_inference(S, dev, K)
+    except Exception as exc:  # noqa: BLE001 -- an extra never costs the bench line
+        out["k_mlp_forward"] = {"error": repr(exc)}
     return out
+
+
+def mlp_inference(S, dev, K):
+    """Row f2's dominant kernel at BASELINE configs[4]: the Q-network of the cfg5 recipe, MLP [98, 256, 128, 64, 16, 6] with PReLU
+    (notebooks/experiment_1v1.ipynb cell 1), evaluated for 131 072 envs in one launch of k_mlp_forward (fp32 FFMA, no tensor cores)
+    plus the weight-repacking launch in front of it.  Compute-bound: reported against the fp32 FFMA peak of the part
+    (148 SMs x 128 lanes x 2 x the SM clock) and beside the torch module (cuBLAS SGEMMs + elementwise passes)."""
+    import torch
+    from torch import nn
+
+    dims, rows = [98, 256, 128, 64, 16, 6], 131072
+    layers = []
+    for i, d in enumerate(dims[:-1]):
+        layers += [nn.Linear(d, dims[i + 1]), nn.PReLU()]
+    net = nn.Sequential(*layers[:-1]).to(dev)
+
+    class Q(nn.Module):  # the reference's MLP keeps its stack in `.model` and ignores the spatial input (dqn.py:72-93)
+        def __init__(self):
+            super().__init__()
+            self.model = net
+
+        def forward(self, spatial, non_spatial):
+            return self.model(non_spatial.view(non_spatial.size(0), -1))
+
+    q = Q()
+    fused = S.FusedMLP(q)
+    x = (torch.rand(rows, 1, dims[0], device=dev) < 0.15).float()
+    sp = torch.zeros(rows, 1, 1, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        evs = []
+        for _ in range(max(K, 10)):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize(dev)
+        return sorted(s.elapsed_time(e) for s, e in evs)[len(evs) // 2]
+
+    flop = 2.0 * rows * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    with torch.no_grad():
+        ms_torch = timed(lambda: q(sp, x))
+        ms = timed(lambda: fused(sp, x))
+        err = float((fused(sp, x) - q(sp, x)).abs().max())
+    sm_mhz = torch.cuda.get_device_properties(dev).clock_rate / 1e3 if hasattr(torch.cuda.get_device_properties(dev), "clock_rate") else 1965.0
+    peak_tf = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    return {"rows": rows, "dims": dims, "ms": ms, "tflops_fp32": flop / ms / 1e9, "fp32_ffma_peak_tflops": peak_tf,
+            "frac_of_fp32_ffma_peak": flop / ms / 1e9 / peak_tf, "torch_module_ms": ms_torch, "max_abs_diff_vs_torch": err,
+            "launches": 2}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
