@@ -85,26 +85,31 @@ class ReplayBuffer:
         return launches * env.num_envs
 
     def _populate_single(self, env, num_steps):
-        step = 0
-        while step < num_steps:  # replay_memory.py:103-143
-            state_sequence = np.zeros((self.trajectory_size, self.state_size))
-            s, _ = env.reset()
-            state = env.flatten_state(s)
-            state_sequence[:] = state
-            done = truncation = False
-            while not done and not truncation:
-                imposters = env.imposter_idxs
-                action = env.sample_actions()
-                n_s, reward, done, truncation, _ = env.step(action)
-                next_state = env.flatten_state(n_s)
-                next_sequence = np.roll(state_sequence.copy(), -1, axis=0)
-                next_sequence[-1] = next_state.copy()
-                self.add(state_sequence, action, reward, next_sequence, done, imposters)
-                state_sequence = next_sequence
-                step += 1
-                if done or step >= num_steps:
+        """Reference mode (one env, one transition per step): whole random-policy episodes until `num_steps` transitions are
+        stored; the last episode is cut where the count is reached (replay_memory.py:103-143)."""
+        added = 0
+        while added < num_steps:
+            for transition in self._random_episode(env):
+                self.add(*transition)
+                added += 1
+                if added >= num_steps:
                     break
-        return step
+        return added
+
+    def _random_episode(self, env):
+        """The transitions of one random-policy episode as `add` takes them.  The T-deep window starts as T copies of the reset
+        state and slides by one state per step (replay_memory.py:107-134); the episode's imposter ids are read before the step."""
+        start = np.asarray(env.flatten_state(env.reset()[0]), dtype=np.float64)
+        window = np.tile(start, (self.trajectory_size, 1))
+        ended = False
+        while not ended:
+            who = env.imposter_idxs
+            action = env.sample_actions()
+            obs, reward, done, truncated, _ = env.step(action)
+            newest = np.asarray(env.flatten_state(obs), dtype=np.float64)
+            slid = np.vstack([window[1:], newest[None, :]])
+            yield window, action, reward, slid, done, who
+            window, ended = slid, bool(done or truncated)
 
     # ---------------------------------------------------------------- batched collection
     def attach(self, env, static_buffers=False):

@@ -153,3 +153,27 @@ def test_cuda_matches_the_reference_directly(cuda_lib, name):
             for (rsp, rns), (gsp, gns) in zip(rf.generate_featurized_states(), feat.generate_featurized_states()):
                 assert np.array_equal(rsp.detach().numpy(), cpu(gsp)) and np.array_equal(rns.detach().numpy(), cpu(gns))
     assert int(cpu(env.episode_stats())[0]) == episodes
+
+
+@pytest.mark.parametrize("T", [1, 3])
+def test_reference_mode_populate_fills_the_ring_like_the_reference_populate(cuda_lib, T):
+    """`sus_net_b200.ReplayBuffer.populate` on a reference-mode env (one env, one transition per step) against the reference's
+    own `ReplayBuffer.populate` (replay_memory.py:96-143) on a twin env with the same seed: same ring contents, index and size,
+    incl. the episode that is cut where the requested count is reached."""
+    import sus_net_b200 as S
+
+    _, replay_mod, _, _, _ = H.import_reference_training()
+    kw = dict(n_crew=2, n_jobs=0, time_step_reward=0, kill_reward=-3, sabotage_reward=0, end_of_game_reward=0, random_state=7)
+    rings = []
+    for cls in (replay_mod.ReplayBuffer, S.ReplayBuffer):
+        env = S.ImposterTrainingGround(**kw)
+        buf = cls(max_size=400, trajectory_size=T, state_size=env.flattened_state_size, n_imposters=env.n_imposters,
+                  n_agents=env.n_agents)
+        for t_ in (buf.states, buf.next_states, buf.rewards, buf.actions, buf.dones, buf.imposters):
+            t_.zero_()
+        buf.populate(env, 250)
+        rings.append(buf)
+    ref, own = rings
+    assert (ref.idx, ref.size) == (own.idx, own.size) == (250, 250)
+    for k in ("states", "actions", "rewards", "next_states", "dones", "imposters"):
+        assert np.array_equal(cpu(getattr(ref, k)), cpu(getattr(own, k))), k
