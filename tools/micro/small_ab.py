@@ -1,3 +1,9 @@
+#!/usr/bin/env python
+"""Headline kernel (cfg4 + Global, fused step + encode) at 65 536 / 131 072 / 1 Mi envs with the library SUSNET_B200_LIB names
+(default: the in-tree build): one line per env count, for A/B runs of two builds in one GPU session.
+
+    SUSNET_B200_LIB=_ab/libother.so python tools/micro/small_ab.py; python tools/micro/small_ab.py
+"""
 import sys, os, json
 sys.path.insert(0, os.getcwd())
 from tools.kernel_sweep import time_fused
