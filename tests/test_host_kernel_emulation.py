@@ -121,3 +121,46 @@ def test_vector_replay_push_equals_scalar_kernel_and_numpy(emu, shape):
                         if T == 1:
                             out, seq_out = _run(fn, L, ins, ring, N, M, idx, T, S, A, n_imp, dtype, off, idx_dev, in_place=True)
                             assert all(np.array_equal(out[k], want[k]) for k in want) and np.array_equal(seq_out, want_seq)
+
+
+def test_mlp_weight_packer_writes_the_chunk_images_the_forward_kernel_copies(tmp_path):
+    """k_mlp_pack on the host: for every layer the image is [column block][16-k chunk][kk][column] with zeros outside the
+    weight matrix -- exactly the [kk][column] tiles the forward kernel's staging buffer holds per chunk (susnet_mlp.cu, `put`)."""
+    from sus_net_b200 import _lib as L
+
+    src = open(os.path.join(ROOT, "sus_net_b200", "csrc", "susnet_mlp.cu")).read()
+    pieces = [re.search(r"constexpr int kKc = 16;[^\n]*\n", src).group(0),
+              re.search(r"struct MlpParams \{.*?\n\};\n", src, re.S).group(0),
+              re.search(r"__host__ __device__ inline int mlp_ct[^\n]*\n", src).group(0),
+              re.search(r"__host__ __device__ inline int64_t mlp_packed_floats.*?\n\}\n", src, re.S).group(0),
+              re.search(r"__global__ void __launch_bounds__\(256\) k_mlp_pack.*?\n\}\n", src, re.S).group(0)]
+    inc = tmp_path / "mlp_pack.inc"
+    inc.write_text("\n".join(pieces))
+    so = str(tmp_path / "mlp_pack_emu.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "emu"),
+                    "-I", os.path.join(ROOT, "include"), f'-DKERNEL_SOURCE="{inc}"',
+                    os.path.join(ROOT, "tests", "emu", "mlp_pack_emu.cpp"), "-o", so], check=True)
+    lib = C.CDLL(so)
+    lib.emu_mlp_pack.argtypes = [C.POINTER(L.SusMlpSpec), C.c_void_p]
+    lib.emu_mlp_pack.restype = None
+    rng = np.random.default_rng(3)
+    for dims in ([98, 256, 128, 64, 16, 6], [4, 6], [200, 150, 17, 129, 3], [5, 65, 1]):
+        ws = [rng.standard_normal((m, k)).astype(np.float32) for k, m in zip(dims[:-1], dims[1:])]
+        spec = L.SusMlpSpec(n_layers=len(ws), activation=L.ACT_RELU)
+        for i, d in enumerate(dims):
+            spec.dims[i] = d
+        for l, w in enumerate(ws):
+            spec.weight[l] = w.ctypes.data
+        want = []
+        for w in ws:
+            m, k = w.shape
+            cb = 16 * (8 if m > 64 else 4 if m > 16 else 1)
+            n_blocks, n_chunks = -(-m // cb), -(-k // 16)
+            padded = np.zeros((n_blocks * cb, n_chunks * 16), np.float32)
+            padded[:m, :k] = w
+            # [block][col][chunk][kk] -> [block][chunk][kk][col]
+            want.append(padded.reshape(n_blocks, cb, n_chunks, 16).transpose(0, 2, 3, 1).ravel())
+        want = np.concatenate(want)
+        got = np.full(want.size, np.nan, np.float32)
+        lib.emu_mlp_pack(C.byref(spec), got.ctypes.data)
+        assert np.array_equal(got, want), dims

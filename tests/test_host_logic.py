@@ -267,3 +267,31 @@ def test_compact_protocol_host_codec_matches_the_numpy_spec(lib):
             assert np.array_equal(got[0].view(np.int64), want[0].view(np.int64)) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
             got32 = cp.decode(r, np.float32)
             assert np.array_equal(got32[0].view(np.int32), want[0].astype(np.float32).view(np.int32))
+
+
+def test_mlp_workspace_size_is_a_host_computation(lib):
+    """sus_mlp_workspace_bytes needs no device: per layer [column blocks of 16 * CT columns] x [chunks of 16 k] floats, zero
+    padded, CT = 8 / 4 / 1 for layers with > 64 / > 16 / <= 16 outputs (the rule the forward kernel stages by); 0 = invalid."""
+    L = lib.lib()
+
+    def spec_of(dims, weights=True):
+        s = lib.SusMlpSpec(n_layers=len(dims) - 1, activation=lib.ACT_PRELU)
+        for i, d in enumerate(dims):
+            s.dims[i] = d
+        for l in range(len(dims) - 1):
+            s.weight[l] = 0x1000 if weights else None  # never dereferenced on the host
+        return s
+
+    def want(dims):
+        total = 0
+        for k, m in zip(dims[:-1], dims[1:]):
+            cb = 16 * (8 if m > 64 else 4 if m > 16 else 1)
+            total += -(-m // cb) * cb * -(-k // 16) * 16
+        return 4 * total
+
+    for dims in ([98, 256, 128, 64, 16, 6], [4, 6], [200, 150, 17, 129, 3], [36, 200, 100, 7], [16, 400, 400, 2]):
+        assert L.sus_mlp_workspace_bytes(C.byref(spec_of(dims))) == want(dims), dims
+    assert want([98, 256, 128, 64, 16, 6]) == 283648
+    assert L.sus_mlp_workspace_bytes(C.byref(spec_of([8, 0, 2]))) == 0          # a layer width < 1
+    assert L.sus_mlp_workspace_bytes(C.byref(spec_of([8, 4, 2], weights=False))) == 0  # NULL weight
+    assert L.sus_mlp_workspace_bytes(None) == 0
