@@ -164,3 +164,260 @@ def test_mlp_weight_packer_writes_the_chunk_images_the_forward_kernel_copies(tmp
         got = np.full(want.size, np.nan, np.float32)
         lib.emu_mlp_pack(C.byref(spec), got.ctypes.data)
         assert np.array_equal(got, want), dims
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The DEVICE code of reset / step / flatten / feature rows, compiled for the host (tests/emu/step_emu.cpp) and held against the
+# oracle: the CPU suite then covers the very functions the kernels run -- reset_env, step_env, agent_reward, finish_one's
+# auto-reset and statistics, write_flat, flat_component (float rows, byte-staged rows, compile-time agent count), the Global /
+# Perspective rows and plane offsets -- not only their restatement.
+@pytest.fixture(scope="module")
+def step_emu(tmp_path_factory):
+    from sus_net_b200 import _lib as L
+
+    d = tmp_path_factory.mktemp("step_emu")
+    src = open(os.path.join(ROOT, "sus_net_b200", "csrc", "susnet_api.cu")).read()
+    pieces = [re.search(r"struct StepParams \{.*?\n\};\n", src, re.S).group(0),
+              src[src.index("__device__ __forceinline__ int reward_row_bytes"):src.index("// K1 (+K2), direct-store path")],
+              src[src.index("// unflatten one row (gymnasium.spaces.unflatten"):src.index("template <typename T>\n__global__ void __launch_bounds__(kThreads) k_encode_rows")],
+              src[src.index("int flat_size(const SusConfig& c) {"):src.index("inline int32_t align128")]]
+    inc = d / "step_glue.inc"
+    inc.write_text("\n".join(pieces))
+    so = str(d / "step_emu.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-I", os.path.join(ROOT, "tests", "emu"),
+                    "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "sus_net_b200", "csrc"),
+                    f'-DKERNEL_SOURCE="{inc}"', os.path.join(ROOT, "tests", "emu", "step_emu.cpp"), "-o", so], check=True)
+    lib = C.CDLL(so)
+    vp = C.c_void_p
+    lib.emu_reset.argtypes = [C.POINTER(L.SusConfig), C.c_uint64, vp, vp, vp, vp]
+    lib.emu_step.argtypes = [C.POINTER(L.SusConfig), C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.emu_export_flat.argtypes = [C.POINTER(L.SusConfig), vp, vp, vp, vp, vp]
+    lib.emu_encode.argtypes = [C.POINTER(L.SusConfig), C.POINTER(L.SusEncodeSpec), C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.emu_encode_rows.argtypes = [C.POINTER(L.SusConfig), C.POINTER(L.SusEncodeSpec), C.c_int, vp, C.c_int64, vp, vp]
+    return lib
+
+
+class _EmuEnv:
+    """Structure-of-arrays env state in numpy + the emulated device functions (what BatchedFourRoomEnv does with kernels)."""
+
+    def __init__(self, lib, cfg, N, seed, env_id_base=0):
+        import oracle
+        from sus_net_b200 import _lib as L
+
+        self.lib, self.N, self.A = lib, N, cfg["n_imposters"] + cfg["n_crew"]
+        kw = {k: (oracle.VARIANT_IDS[v] if k == "variant" else (int(v) if isinstance(v, bool) else v)) for k, v in cfg.items()}
+        self.cfg = L.SusConfig(num_envs=N, seed=seed, env_id_base=env_id_base, auto_reset=1, **kw)
+        self.S = oracle.flat_size(cfg)
+        self.pos, self.jobpos = np.zeros(N, np.uint64), np.zeros(N, np.uint64)
+        self.aux, self.met = np.zeros((N, 4), np.uint32), np.zeros((N, 4), np.uint32)
+        self.stats = np.zeros(10, np.uint64)
+        self.err = np.zeros(1, np.uint32)
+        self.step_tick = self.reset_epoch = 0
+
+    def _state(self):
+        return [a.ctypes.data for a in (self.pos, self.jobpos, self.aux, self.met)]
+
+    def reset(self):
+        self.lib.emu_reset(C.byref(self.cfg), self.reset_epoch, *self._state())
+        self.reset_epoch += 1
+        return self.flat_states()
+
+    def imposter_mask(self):
+        return ((self.aux[:, 0:1] >> 8 >> np.arange(self.A, dtype=np.uint32)[None, :]) & 1).astype(np.uint8)
+
+    def flat_states(self):
+        out = np.zeros((self.N, self.S), np.int64)
+        self.lib.emu_export_flat(C.byref(self.cfg), *self._state(), out.ctypes.data)
+        return out
+
+    def step(self, actions=None):
+        a = None if actions is None else np.ascontiguousarray(actions, np.int32)
+        r = np.zeros((self.N, self.A), np.float64)
+        done, trunc = np.zeros(self.N, np.uint8), np.zeros(self.N, np.uint8)
+        nf = np.zeros((self.N, self.S), np.float32)
+        a_out = np.zeros((self.N, self.A), np.int32)
+        self.lib.emu_step(C.byref(self.cfg), self.step_tick, *self._state(), None if a is None else a.ctypes.data, r.ctypes.data,
+                          done.ctypes.data, trunc.ctypes.data, nf.ctypes.data, a_out.ctypes.data, self.stats.ctypes.data,
+                          self.err.ctypes.data)
+        self.step_tick += 1
+        return dict(rewards=r, done=done, trunc=trunc, next_flat=nf.astype(np.int64), actions=a_out)
+
+    def encode(self, kind, components=(), mode=0, rows=None):
+        """Feature tensors of the live envs, or (rows = (n, S) int64 flattened states) of replay rows like fit()."""
+        import oracle
+        from sus_net_b200 import _lib as L
+
+        spec = L.SusEncodeSpec(kind=kind, n_components=len(components))
+        for i, name in enumerate(components):
+            spec.components[i] = oracle.FLAT_COMPONENTS[name]
+        shape = L.SusEncodeShape()
+        assert L.lib().sus_encode_shape(C.byref(self.cfg), C.byref(spec), C.byref(shape)) == 0
+        n = self.N if rows is None else rows.shape[0]
+        sp = np.full((max(shape.spatial_views, 1), n, max(shape.spatial_floats, 1)), np.nan, np.float32)
+        ns = np.full((shape.non_spatial_views, n, shape.non_spatial_floats), np.nan, np.float32)
+        if rows is None:
+            rc = self.lib.emu_encode(C.byref(self.cfg), C.byref(spec), mode, *self._state(), sp.ctypes.data, ns.ctypes.data)
+        else:
+            rows = np.ascontiguousarray(rows, np.int64)
+            rc = self.lib.emu_encode_rows(C.byref(self.cfg), C.byref(spec), mode, rows.ctypes.data, n, sp.ctypes.data, ns.ctypes.data)
+        assert rc == 0
+        return sp, ns
+
+
+def _all_cases():
+    from tests.cases import CASES, EDGE_CASES
+
+    return {**CASES, **EDGE_CASES}
+
+
+def _case_ids():
+    return sorted(_all_cases())
+
+
+@pytest.mark.parametrize("case", _case_ids())
+def test_device_step_code_on_the_host_equals_the_oracle(step_emu, case):
+    """The 12 canonical and 8 edge configurations (1-step episodes, 1-step vote windows, 8 agents x 8 jobs, all-zero rewards incl.
+    -0.0): reset + 220 fused random-policy steps (every 7th with explicit sampled actions) of 96 envs: flat states, float64 reward
+    bit patterns, done / truncated, the actions the fused policy drew, auto-reset states and the episode statistics."""
+    import oracle
+
+    cfg = _all_cases()[case]
+    N, seed = 96, 11
+    emu, orc = _EmuEnv(step_emu, cfg, N, seed), oracle.OracleEnv(cfg, N, seed=seed)
+    assert np.array_equal(emu.reset(), orc.reset())
+    for t in range(220):
+        acts = orc.sample_actions() if t % 7 == 3 else None
+        want, got = orc.step(acts), emu.step(acts)
+        assert np.array_equal(got["next_flat"], want["next_flat"]), (case, t)
+        assert np.array_equal(got["rewards"].view(np.int64), want["rewards"].view(np.int64)), (case, t)
+        assert np.array_equal(got["done"], want["done"]) and np.array_equal(got["trunc"], want["trunc"]), (case, t)
+        assert np.array_equal(got["actions"], want["actions"]), (case, t)
+        assert np.array_equal(emu.flat_states(), orc.flat_states()), (case, t)
+    assert np.array_equal(emu.stats.astype(np.int64), orc.stats()) and int(emu.err[0]) == 0
+    # (random play rarely ends an ImposterTrainingGround episode with 3-4 crew inside 220 steps; every other case finishes some)
+    assert int(emu.stats[0]) > 0 or cfg["variant"] == "training_ground"
+
+
+def test_device_feature_rows_on_the_host_equal_the_oracle(step_emu):
+    """Flat rows (float rows, byte-staged rows, byte-staged rows built with the compile-time agent count), Global and Perspective
+    non-spatial rows and planes, on states taken along oracle trajectories."""
+    import oracle
+    from sus_net_b200 import _lib as L
+    from tests.cases import CASES, FLAT_COMPONENT_SETS, FLAT_COMPONENT_SETS_TAGGING, GLOBAL_CASES
+
+    def walk(case):
+        cfg = CASES[case]
+        emu = _EmuEnv(step_emu, cfg, 64, 5)
+        emu.reset()
+        for t in range(60):
+            emu.step(None)
+            if t % 20 == 19:
+                yield cfg, emu, emu.flat_states()
+
+    for case, sets in {**FLAT_COMPONENT_SETS, **FLAT_COMPONENT_SETS_TAGGING}.items():
+        for cfg, emu, flat in walk(case):
+            for comps in sets:
+                want = oracle.encode_flat(cfg, comps, flat)
+                for mode in ((0,) if "scent" in comps else (0, 1, 2)):  # the float-valued scent row is never byte-staged
+                    got = emu.encode(L.ENCODE_FLAT, comps, mode)[1][0]
+                    assert np.array_equal(got, want), (case, comps, mode)
+    for case in GLOBAL_CASES:
+        for cfg, emu, flat in walk(case):
+            A = cfg["n_imposters"] + cfg["n_crew"]
+            sp, ns = oracle.encode_global(cfg, flat)
+            got_sp, got_ns = emu.encode(L.ENCODE_GLOBAL)
+            assert np.array_equal(got_sp[0].reshape(-1, A + 2, 9, 9), sp) and np.array_equal(got_ns, ns), case
+            sp, ns = oracle.encode_perspective(cfg, flat)
+            got_sp, got_ns = emu.encode(L.ENCODE_PERSPECTIVE)
+            assert np.array_equal(got_sp.reshape(A, -1, A + 2, 9, 9), sp) and np.array_equal(got_ns, ns), case
+
+
+def _philox_fixtures():
+    from tests.util import golden_files
+
+    return golden_files("philox")
+
+
+@pytest.mark.parametrize("path", _philox_fixtures(), ids=lambda p: os.path.basename(p).split(".")[0])
+def test_device_step_code_on_the_host_equals_the_reference_fixtures(step_emu, path):
+    """The same device code against outputs of the UNMODIFIED reference (tests/golden/*.philox.npz, minted by
+    tools/make_golden.py on the Philox draws): reset states and roles, then per step the state, the float64 reward bit patterns,
+    done / truncated, the post-auto-reset state and roles."""
+    from tests.cases import CASES
+    from tests.util import case_of, load, reward_bits
+
+    g = load(path)
+    cfg = CASES[case_of(path)]
+    T, N, A = g["actions"].shape
+    emu = _EmuEnv(step_emu, cfg, N, int(g["seed"]), env_id_base=int(g["env_id_base"]))
+    assert np.array_equal(emu.reset(), g["reset_flat"])
+    assert np.array_equal(emu.imposter_mask(), g["reset_imp"].astype(np.uint8))
+    for t in range(T):
+        o = emu.step(g["actions"][t])
+        assert np.array_equal(o["next_flat"], g["next_flat"][t]), f"state differs at step {t}"
+        assert np.array_equal(reward_bits(o["rewards"]), reward_bits(g["rewards"][t])), f"rewards differ at step {t}"
+        assert np.array_equal(o["done"], g["done"][t]) and np.array_equal(o["trunc"], g["trunc"][t])
+        assert np.array_equal(emu.flat_states(), g["cur_flat"][t]), f"post-reset state differs at step {t}"
+        assert np.array_equal(emu.imposter_mask(), g["imp"][t].astype(np.uint8))
+    fin = (g["done"] | g["trunc"]) != 0
+    assert int(emu.stats[0]) == fin.sum() and int(emu.stats[9]) == (g["trunc"] != 0).sum() and int(emu.err[0]) == 0
+
+
+def _feature_fixtures():
+    from tests.util import golden_files
+
+    return golden_files("features")
+
+
+@pytest.mark.parametrize("path", _feature_fixtures(), ids=lambda p: os.path.basename(p).split(".")[0])
+def test_device_feature_rows_on_the_host_equal_the_reference_fixtures(step_emu, path):
+    """The device featurizer code on replay rows (parse_row, the fit() path) against the UNMODIFIED reference's featurizers
+    (tests/golden/*.features.npz): Global and Perspective planes and rows, every flat component list incl. the float scent one
+    (bit patterns), byte-staged rows where the list is integer-valued."""
+    from sus_net_b200 import _lib as L
+    from tests.cases import CASES
+    from tests.util import case_of, load
+
+    g = load(path)
+    cfg = CASES[case_of(path)]
+    flat = g["flat"].astype(np.int64)
+    A = cfg["n_imposters"] + cfg["n_crew"]
+    emu = _EmuEnv(step_emu, cfg, 1, 0)
+    if "global_spatial" in g:
+        sp, ns = emu.encode(L.ENCODE_GLOBAL, rows=flat)
+        assert np.array_equal(sp[0].reshape(-1, A + 2, 9, 9), g["global_spatial"].astype(np.float32))
+        assert np.array_equal(ns, g["global_non_spatial"])
+        sp, ns = emu.encode(L.ENCODE_PERSPECTIVE, rows=flat)
+        assert np.array_equal(sp.reshape(A, -1, A + 2, 9, 9), g["perspective_spatial"].astype(np.float32))
+        assert np.array_equal(ns, g["perspective_non_spatial"])
+    i = 0
+    while f"flat{i}" in g:
+        comps = [str(c) for c in g[f"flat{i}_components"]]
+        for mode in ((0,) if "scent" in comps else (0, 1, 2)):
+            out = emu.encode(L.ENCODE_FLAT, comps, mode, rows=flat)[1][0]
+            assert np.array_equal(out.view(np.int32), g[f"flat{i}"].view(np.int32)), (comps, mode)
+        i += 1
+
+
+def test_device_step_code_on_the_host_equals_the_oracle_on_random_configurations(step_emu):
+    """24 random constructor-argument sets (every variant, up to 8 agents / 8 jobs, non-integer reward constants, short episodes
+    and vote windows): 150 steps of 40 envs each, everything the step returns and the episode statistics."""
+    import oracle
+    from tests.cases import random_case
+
+    rng = np.random.default_rng(2026)
+    episodes = 0
+    for k in range(24):
+        cfg = random_case(rng)
+        emu, orc = _EmuEnv(step_emu, cfg, 40, 100 + k, env_id_base=7 * k), oracle.OracleEnv(cfg, 40, seed=100 + k, env_id_base=7 * k)
+        assert np.array_equal(emu.reset(), orc.reset()), cfg
+        for t in range(150):
+            acts = orc.sample_actions() if t % 5 == 2 else None
+            want, got = orc.step(acts), emu.step(acts)
+            assert np.array_equal(got["next_flat"], want["next_flat"]), (cfg, t)
+            assert np.array_equal(got["rewards"].view(np.int64), want["rewards"].view(np.int64)), (cfg, t)
+            assert np.array_equal(got["done"], want["done"]) and np.array_equal(got["trunc"], want["trunc"]), (cfg, t)
+            assert np.array_equal(emu.flat_states(), orc.flat_states()), (cfg, t)
+        assert np.array_equal(emu.stats.astype(np.int64), orc.stats()), cfg
+        episodes += int(emu.stats[0])
+    assert episodes > 1000
