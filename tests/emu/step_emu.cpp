@@ -77,6 +77,30 @@ extern "C" int emu_step(const SusConfig* cfg, uint64_t tick, uint64_t* pos, uint
   return 0;
 }
 
+// the same launch through the compact host protocol: bit-packed action records in, reward codes + done / truncated bits out
+extern "C" int emu_step_compact(const SusConfig* cfg, uint64_t tick, uint64_t* pos, uint64_t* jobpos, uint4* aux, uint4* met,
+                                const uint8_t* packed_actions, uint8_t* packed_out, unsigned long long* stats, uint32_t* err) {
+  StepParams p;
+  std::memset(&p, 0, sizeof(p));
+  make_dev_config(*cfg, p.c);
+  make_dev_encode(*cfg, nullptr, p.enc, nullptr);
+  SusCompactLayout cl;
+  compact_layout(*cfg, cl);
+  p.st = StateArrays{pos, jobpos, aux, met};
+  p.actions = packed_actions; p.actions_dtype = SUS_PACKED;
+  p.packed_out = packed_out;
+  p.action_bits = cl.action_bits; p.action_bytes = cl.action_bytes; p.reward_bits = cl.reward_bits; p.result_bytes = cl.result_bytes;
+  p.stats = stats; p.err = err; p.tick = tick; p.N = cfg->num_envs;
+  GridTables tb;
+  tables_of(p.c, tick, tb);
+  switch (cfg->variant) {
+    case SUS_VARIANT_BASE: step_all<SUS_VARIANT_BASE>(p, tb); break;
+    case SUS_VARIANT_TAGGING: step_all<SUS_VARIANT_TAGGING>(p, tb); break;
+    default: step_all<SUS_VARIANT_TRAINING_GROUND>(p, tb); break;
+  }
+  return 0;
+}
+
 extern "C" int emu_export_flat(const SusConfig* cfg, uint64_t* pos, uint64_t* jobpos, uint4* aux, uint4* met, long long* out) {
   DevConfig c;
   make_dev_config(*cfg, c);

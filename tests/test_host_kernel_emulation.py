@@ -191,6 +191,7 @@ def step_emu(tmp_path_factory):
     vp = C.c_void_p
     lib.emu_reset.argtypes = [C.POINTER(L.SusConfig), C.c_uint64, vp, vp, vp, vp]
     lib.emu_step.argtypes = [C.POINTER(L.SusConfig), C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.emu_step_compact.argtypes = [C.POINTER(L.SusConfig), C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.emu_export_flat.argtypes = [C.POINTER(L.SusConfig), vp, vp, vp, vp, vp]
     lib.emu_encode.argtypes = [C.POINTER(L.SusConfig), C.POINTER(L.SusEncodeSpec), C.c_int, vp, vp, vp, vp, vp, vp]
     lib.emu_encode_rows.argtypes = [C.POINTER(L.SusConfig), C.POINTER(L.SusEncodeSpec), C.c_int, vp, C.c_int64, vp, vp]
@@ -241,6 +242,15 @@ class _EmuEnv:
                           self.err.ctypes.data)
         self.step_tick += 1
         return dict(rewards=r, done=done, trunc=trunc, next_flat=nf.astype(np.int64), actions=a_out)
+
+    def step_compact(self, proto, actions):
+        """One step through the compact host protocol: the library's host packer, the device code, the library's host decoder."""
+        packed = proto.pack_actions(np.ascontiguousarray(actions, np.int32))
+        rec = np.zeros((self.N, proto.result_bytes), np.uint8)
+        self.lib.emu_step_compact(C.byref(self.cfg), self.step_tick, *self._state(), packed.ctypes.data, rec.ctypes.data,
+                                  self.stats.ctypes.data, self.err.ctypes.data)
+        self.step_tick += 1
+        return proto.decode(rec)
 
     def encode(self, kind, components=(), mode=0, rows=None):
         """Feature tensors of the live envs, or (rows = (n, S) int64 flattened states) of replay rows like fit()."""
@@ -421,3 +431,115 @@ def test_device_step_code_on_the_host_equals_the_oracle_on_random_configurations
         assert np.array_equal(emu.stats.astype(np.int64), orc.stats()), cfg
         episodes += int(emu.stats[0])
     assert episodes > 1000
+
+
+@pytest.mark.parametrize("case", _case_ids())
+def test_device_step_code_through_the_compact_host_protocol_equals_the_oracle(step_emu, case):
+    """Bit-packed action records in, reward codes + done / truncated bits out (SUS_PACKED / SusStepIO.packed_out): packed by
+    sus_host_pack_actions, stepped by the device code, decoded by sus_host_decode_results -- the float64 rewards must carry the
+    oracle's bit patterns (incl. -0.0 and non-integer constants), an env whose action is rejected reports NaN and stays put."""
+    import types
+
+    import oracle
+    from sus_net_b200 import _lib as L
+    from sus_net_b200.compact import CompactProtocol
+
+    cfg = _all_cases()[case]
+    N, seed = 64, 3
+    emu, orc = _EmuEnv(step_emu, cfg, N, seed), oracle.OracleEnv(cfg, N, seed=seed)
+    proto = CompactProtocol(types.SimpleNamespace(lib=L.lib(), _cfg=emu.cfg, n_agents=emu.A))
+    assert np.array_equal(emu.reset(), orc.reset())
+    for t in range(120):
+        acts = orc.sample_actions()
+        want = orc.step(acts)
+        r, d, tr = emu.step_compact(proto, acts)
+        assert np.array_equal(r.view(np.int64), want["rewards"].view(np.int64)), (case, t)
+        assert np.array_equal(d, want["done"] != 0) and np.array_equal(tr, want["trunc"] != 0), (case, t)
+        assert np.array_equal(emu.flat_states(), orc.flat_states()), (case, t)
+    assert np.array_equal(emu.stats.astype(np.int64), orc.stats())
+    # a role-list index past the end of the crew list (the imposter list is the longer one): rejected, counted, NaN, state kept
+    before = emu.flat_states()
+    bad = orc.sample_actions()
+    crew = np.argwhere(orc.imposter_mask()[0] == 0)[0, 0]
+    bad[0, crew] = oracle.n_role_actions(cfg, False)
+    r, d, tr = emu.step_compact(proto, bad)
+    assert np.isnan(r[0]).all() and not d[0] and not tr[0] and int(emu.err[0]) == 1
+    assert np.array_equal(emu.flat_states()[0], before[0])
+
+
+@pytest.fixture(scope="module")
+def policy_emu(tmp_path_factory):
+    from sus_net_b200 import _lib as L
+
+    d = tmp_path_factory.mktemp("policy_emu")
+    pol = open(os.path.join(ROOT, "sus_net_b200", "csrc", "susnet_policy.cu")).read()
+    api = open(os.path.join(ROOT, "sus_net_b200", "csrc", "susnet_api.cu")).read()
+    pieces = [pol[pol.index("constexpr uint32_t P_POLICY"):pol.index("}  // namespace")],
+              api[api.index("int flat_size(const SusConfig& c) {"):api.index("int component_size(const SusConfig& c, int comp)")]]
+    inc = d / "policy.inc"
+    inc.write_text("\n".join(pieces))
+    so = str(d / "policy_emu.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-I", os.path.join(ROOT, "tests", "emu"),
+                    "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "sus_net_b200", "csrc"),
+                    f'-DKERNEL_SOURCE="{inc}"', os.path.join(ROOT, "tests", "emu", "policy_emu.cpp"), "-o", so], check=True)
+    lib = C.CDLL(so)
+    vp = C.c_void_p
+    lib.emu_select_actions.argtypes = [C.POINTER(L.SusConfig), C.c_uint64, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp]
+    lib.emu_seq_roll.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int]
+    return lib
+
+
+@pytest.mark.parametrize("case", ["cfg4_base_1v4", "cfg4alt_itg_1v4", "cfg3_tagging_1v2", "base_2v3_j3", "tagging_2v5_short"])
+def test_selection_kernel_on_the_host_equals_the_numpy_restatement(step_emu, policy_emu, case):
+    """k_select_actions (the acting part of train(), train.py:349-381): epsilon-greedy with Philox draws, role-aware ranges, first
+    argmax on ties, dead agents keep 0, both imposter Q layouts, eps as a scalar or from memory, int32 / uint8 actions."""
+    import oracle
+    from sus_net_b200 import _lib as L
+
+    cfg = _all_cases()[case]
+    N, seed, base = 300, 17, 555
+    env = _EmuEnv(step_emu, cfg, N, seed, env_id_base=base)
+    env.reset()
+    for _ in range(25):
+        env.step(None)  # some agents die, some episodes restart
+    A, nI = env.A, cfg["n_imposters"]
+    nia, nca = oracle.n_role_actions(cfg, True), oracle.n_role_actions(cfg, False)
+    rng = np.random.default_rng(3)
+    ids = np.arange(base, base + N)
+    flat = env.flat_states()
+    for trial, (eps, use_imp, use_crew, per_view, dtype) in enumerate([
+            (0.0, True, True, nI != 1, np.int32), (0.3, True, True, True, np.uint8), (1.0, True, True, nI != 1, np.int32),
+            (0.2, True, False, nI != 1, np.int32), (0.0, False, True, True, np.uint8), (0.5, False, False, True, np.int32)]):
+        q_imp = rng.standard_normal((A, N, nia) if per_view else (N, nia)).astype(np.float32) if use_imp else None
+        q_crew = rng.standard_normal((A, N, nca)).astype(np.float32) if use_crew else None
+        if q_imp is not None:
+            q_imp[..., 3] = q_imp[..., 1]  # ties: the FIRST maximum wins (torch.argmax, train.py:368-370)
+        eps_arr = np.array([eps], np.float32)
+        out = np.full((N, A), 77, dtype)
+        policy_emu.emu_select_actions(C.byref(env.cfg), trial, env.aux.ctypes.data, None if q_imp is None else q_imp.ctypes.data,
+                                      None if q_crew is None else q_crew.ctypes.data, eps_arr.ctypes.data if trial % 2 else None,
+                                      eps, int(per_view), L.U8 if dtype == np.uint8 else L.I32, out.ctypes.data)
+        want = oracle.select_actions(cfg, seed, ids, trial, flat[:, 2 * A:3 * A], env.imposter_mask(), q_imp, q_crew, eps,
+                                     imposter_per_view=per_view)
+        assert np.array_equal(out.astype(np.int32), want), (case, trial)
+
+
+def test_feature_sequence_roll_on_the_host_equals_numpy(policy_emu):
+    """k_seq_roll (np.roll of T-deep ENCODED feature sequences, restart from T copies where the episode ended,
+    train.py:388-389,440-445): the 128-bit and the scalar variant against numpy, view-major rows."""
+    rng = np.random.default_rng(0)
+    for views, n_envs, T, R in ((1, 37, 1, 8), (5, 40, 3, 16), (2, 19, 4, 7), (3, 64, 2, 567)):
+        rows = views * n_envs
+        seq = rng.standard_normal((rows, T, R)).astype(np.float32)
+        newest = rng.standard_normal((rows, R)).astype(np.float32)
+        done = (rng.random(n_envs) < 0.3).astype(np.uint8)
+        trunc = (rng.random(n_envs) < 0.2).astype(np.uint8)
+        fin = np.tile((done | trunc).astype(bool), views)
+        want = np.roll(seq, -1, axis=1)
+        want[:, -1] = newest
+        want[fin] = newest[fin][:, None, :]
+        for vec in ((0, 1) if R % 4 == 0 else (0,)):
+            out = np.full_like(seq, np.nan)
+            policy_emu.emu_seq_roll(seq.ctypes.data, out.ctypes.data, newest.ctypes.data, done.ctypes.data, trunc.ctypes.data, rows,
+                                    n_envs, T, R, vec)
+            assert np.array_equal(out, want), (views, n_envs, T, R, vec)
