@@ -1,7 +1,8 @@
-// Host stand-in for <cuda_runtime.h>: just enough to compile the device code of this library with g++ and run it one emulated
-// thread at a time (tests/test_host_kernel_emulation.py).  Warp collectives have the semantics of a warp whose other lanes
-// contribute nothing (any = own predicate, reduce = own value, shuffles from other lanes = 0), atomics are plain updates: valid
-// for code in which lanes only meet in order-independent accumulations.  Test infrastructure only; never part of the product.
+// Host stand-in for <cuda_runtime.h>: just enough to compile the device code of this library with g++.  Default mode: one
+// emulated thread at a time (tests/test_host_kernel_emulation.py) -- warp collectives have the semantics of a warp whose other
+// lanes contribute nothing (any = own predicate, reduce = own value, shuffles from other lanes = 0), atomics are plain updates:
+// valid for code in which lanes only meet in order-independent accumulations.  With EMU_SIMT the threads of a block are fibers
+// and barriers / collectives are real (simt.h, tests/test_host_simt_emulation.py).  Test infrastructure only.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -43,10 +44,14 @@ static inline double __longlong_as_double(long long v) { double d; std::memcpy(&
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline void __threadfence() {}
+#ifdef EMU_SIMT  // whole kernels: threads are fibers, barriers and warp collectives switch between them (simt.h)
+#include "simt.h"
+#else            // one thread at a time: barriers are no-ops, a warp is its calling lane
 static inline void __syncthreads() {}
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T, int) { return T(0); }
+#endif
 template <typename T> static inline T atomicAdd(T* p, T v) { const T old = *p; *p = old + v; return old; }
 static inline unsigned atomicAdd(volatile unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; return old; }
